@@ -1,0 +1,144 @@
+/*
+ * lemon_b200.h — C ABI of liblemon_b200.so: the B200 (sm_100a) implementation of the
+ * LEMoN pair-scoring hot path.
+ *
+ * Reference interfaces replaced (all under MLforHealth/LEMoN):
+ *   normalize_vectors                         lib/utils/utils.py:39-40      -> lemon_normalize_cast
+ *   dists_tr / d_1 row-wise distances         run_lemon.py:169,173,250-253  -> lemon_rowwise_dist
+ *   faiss.IndexFlatIP/L2 .add/.search         run_lemon.py:167-176,235-236  -> lemon_knn_candidates (tcgen05)
+ *                                                                              + lemon_rerank (fp32 exact re-rank)
+ *                                                                              + lemon_knn_exact (fp32 fallback)
+ *   per-sample loop                           run_lemon.py:238-307          -> lemon_score
+ *   calc_scores_given_hparams_vectorized      lib/metrics/utils.py:47-82    -> lemon_score / lemon_combine_scores
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer owned by the caller; the library allocates only
+ *     the scratch held by its ctx;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on
+ *     success or a negative lemon_status, never throws and never synchronises (except
+ *     ctx create/destroy);
+ *   - one ctx per device; a ctx is not thread-safe, different ctxs are independent;
+ *   - DB row indices are int32 on the device (M < 2^31); the Python layer widens to int64
+ *     where faiss does;
+ *   - metric: 0 = inner product (descending, faiss IndexFlatIP), 1 = squared L2 (ascending,
+ *     faiss IndexFlatL2).
+ *   - "top list" = per query row `kp` entries sorted best-first under the documented total
+ *     order (value best-first, then DB index ascending); missing entries are idx = -1,
+ *     val = -inf (IP) / +inf (L2), as faiss pads.
+ */
+#ifndef LEMON_B200_H_
+#define LEMON_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lemon_ctx lemon_ctx;
+
+enum lemon_status {
+  LEMON_OK = 0,
+  LEMON_ERR_INVALID = -1,     /* bad argument (shape, alignment, unsupported d/k) */
+  LEMON_ERR_CUDA = -2,        /* a CUDA runtime/driver call failed; see lemon_last_error */
+  LEMON_ERR_UNSUPPORTED = -3  /* device is not sm_100 / feature not available */
+};
+
+enum lemon_metric { LEMON_METRIC_IP = 0, LEMON_METRIC_L2 = 1 };
+
+#define LEMON_KPRIME 64          /* candidates kept per (row, DB segment) by the tensor-core kernel */
+#define LEMON_MAX_KP 64          /* largest k (+1 for self-exclusion) a top list can hold */
+#define LEMON_MAX_D_TC 768       /* largest padded dim the tensor-core kernel keeps resident */
+
+int lemon_version(void);
+int lemon_ctx_create(int device, lemon_ctx** out);
+int lemon_ctx_destroy(lemon_ctx* ctx);
+const char* lemon_last_error(lemon_ctx* ctx);
+
+/* Row-wise L2 normalisation + 16-bit operand copy (K0).
+ *   in        [n, d]  fp32
+ *   out_f32   [n, d]  fp32, x / max(||x||, 1e-12) when do_normalize, else a copy (may alias `in`; may be NULL)
+ *   out_f16   [n, d16] fp16, the (normalised) row rounded to nearest, zero padded to d16 (multiple of 64; may be NULL)
+ *   row_stats [n, 4]  fp32 per row: {||x||, ||fp16(x)||, ||x - fp16(x)||, ||x||^2} of the OUTPUT row (may be NULL)
+ *   stats_max [4]     fp32, running maxima over rows of {||x||, ||fp16(x)||, ||x - fp16(x)||, | ||x||^2 - 1 |};
+ *                     caller zero-initialises (may be NULL)
+ */
+int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* out_f16,
+                         float* row_stats, float* stats_max, int64_t n, int d, int d16,
+                         int do_normalize, void* stream);
+
+/* out[i] = 1 - <a_i, b_i> (metric IP / cosine)  or  sum (a_i - b_i)^2 (metric L2). run_lemon.py:169,173,250-253 */
+int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* out,
+                       int64_t n, int d, int metric, void* stream);
+
+/* Tensor-core candidate search (K1): fp16 operands, fp32 TMEM accumulation, streaming top-64
+ * fused into the epilogue; the nq x m similarity matrix never reaches HBM.
+ *   q16  [nq, d16], db16 [m, d16]  fp16 row-major, d16 % 64 == 0, d16 <= LEMON_MAX_D_TC
+ *   nseg  number of DB segments scanned independently (load balance for small nq); >= 1
+ *   cand_val / cand_idx [nq, nseg * LEMON_KPRIME]: per segment the 64 best approximate inner
+ *   products, sorted descending (ties: lower DB index first); -inf / -1 padding.
+ *   cta_group: 1 or 2 (2 = cta_group::2 CTA pairs, 256 query rows per pair); 0 = library default.
+ */
+int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
+                         int d16, int nseg, int cta_group, float* cand_val, int32_t* cand_idx,
+                         void* stream);
+
+/* fp32 exact re-rank of the candidates + per-row certificate (K2a).
+ *   q [nq, d], db [m, d] fp32;  cand_* [nq, ncand] from lemon_knn_candidates (ncand = nseg*64)
+ *   q_row_stats [nq,4], db_stats_max [4]: outputs of lemon_normalize_cast for the query rows and the DB.
+ *   They give the rigorous per-row bound on |fp16 tensor-core inner product - exact|:
+ *     eps_row = ||q - q16|| * max||b16|| + ||q|| * max||b - b16|| + acc_eps
+ *   (Cauchy-Schwarz on the two rounding-error vectors; acc_eps covers fp32 accumulation).  NULL = eps 0.
+ *   Metric L2 ranks by -||q-b||^2 = 2<q,b> - ||q||^2 - ||b||^2; the bound then uses ||q||^2 from
+ *   q_row_stats and min||b||^2 >= 1 - db_stats_max[3].
+ *   top_val / top_idx [nq, kp]: exact top list.  A row is certified when its kp-th exact value
+ *   beats every non-candidate's bound (each segment's 64th approximate value + eps_row); otherwise its
+ *   row id is appended to uncert_rows[0 .. *n_uncert) (caller zeroes *n_uncert; room for nq ids).
+ */
+int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const float* cand_val,
+                 const int32_t* cand_idx, const float* q_row_stats, const float* db_stats_max,
+                 float acc_eps, int64_t nq, int64_t m, int d, int ncand, int nseg, int kp,
+                 int metric, float* top_val, int32_t* top_idx, int32_t* uncert_rows,
+                 int32_t* n_uncert, void* stream);
+
+/* fp32 brute-force exact kNN on CUDA cores (GPU fallback for uncertified rows, and the
+ * general path for shapes the tensor-core kernel does not take).
+ *   rows: NULL = all nq rows; else a device list of row ids with its length in *n_rows (device).
+ *   max_rows: upper bound of *n_rows (sizes the grid; nq when rows == NULL).
+ *   Writes the top list of each processed row into top_val/top_idx [nq, kp].
+ */
+int lemon_knn_exact(lemon_ctx* ctx, const float* q, const float* db, const int32_t* rows,
+                    const int32_t* n_rows, int64_t max_rows, int64_t nq, int64_t m, int d, int kp,
+                    int metric, float* top_val, int32_t* top_idx, void* stream);
+
+/* Per-sample records + score (K2b): restates run_lemon.py:250-307 and utils.py:63-77 for given top lists.
+ *   xq,yq [nq,d]  image/text query rows;  xdb,ydb [m,d] image/text DB rows;  dists_tr [m]
+ *   topn_* / topm_* [nq, kp]: image-kNN / text-kNN top lists, kp = k + 1 when query_in_db != NULL else k
+ *   query_in_db [nq] int64 or NULL: train-split rule (>=0: drop rank 0, -1: drop the last)
+ *   label_q [nq], label_db [m] int32 or NULL: discrete text metric (--use_discrete_for_text)
+ *   hp[6] = {beta, gamma, tau_1_n, tau_2_n, tau_1_m, tau_2_m}: HOST pointer read at call time, or NULL
+ *   (then sn/sm/score are not written)
+ *   outputs (any may be NULL): d1 [nq]; Dn,dists_n,dists_tr_n,Dm,dists_m,dists_tr_m [nq,k] fp32;
+ *   In, Im [nq,k] int64;  sn, sm, score [nq] float64.
+ */
+int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* xdb, const float* ydb,
+                const float* dists_tr, const float* topn_val, const int32_t* topn_idx,
+                const float* topm_val, const int32_t* topm_idx, const int64_t* query_in_db,
+                const int32_t* label_q, const int32_t* label_db, int64_t nq, int64_t m, int d, int k,
+                int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
+                float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, int64_t* In,
+                int64_t* Im, double* sn, double* sm, double* score, void* stream);
+
+/* Score combination only (lib/metrics/utils.py:63-77) on stacked [n,k] fp32 columns. */
+int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_n, const float* dists_n,
+                         const float* Dm, const float* dists_tr_m, const float* dists_m,
+                         const double* d1, int64_t n, int k, const double* hp /* HOST [6] */, double* sn,
+                         double* sm, double* score, void* stream);
+
+/* Number of kernels this library has launched through `ctx` since creation (bench "gpu_launches"). */
+int64_t lemon_launch_count(lemon_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEMON_B200_H_ */

@@ -1,0 +1,31 @@
+"""lemon_b200 — B200-native (sm_100a) implementation of the LEMoN pair-scoring hot path.
+
+Public surface (mirrors the reference's seams):
+  score_pairs(...)                                  fused replacement of run_lemon.py:163-314,406-407
+  LemonScorer                                       set_database / score / knn / combine_scores
+  faiss_compat.IndexFlatIP / IndexFlatL2            drop-in for the faiss calls at run_lemon.py:167-176,235-236
+  metrics_compat.calc_scores_given_hparams_vectorized   drop-in for lib/metrics/utils.py:47-82
+  dist.score_pairs_sharded                          row-sharded multi-GPU driver (one NCCL all-gather)
+"""
+from . import _lib
+from ._lib import LemonError, LIB_PATH
+from .scoring import LemonScorer, score_pairs, get_scorer, plan_segments, HP_KEYS
+
+__all__ = ["LemonScorer", "score_pairs", "get_scorer", "plan_segments", "LemonError", "LIB_PATH", "HP_KEYS",
+           "install_faiss_shim", "patch_reference_metrics"]
+
+
+def install_faiss_shim():
+    """``import faiss`` in the reference then resolves to lemon_b200.faiss_compat."""
+    import sys
+    from . import faiss_compat
+    sys.modules["faiss"] = faiss_compat
+    return faiss_compat
+
+
+def patch_reference_metrics(ref_metrics_utils_module):
+    """Monkey-patch the reference's ``lib.metrics.utils`` so its callers (run_lemon.py:406,
+    optim_func at utils.py:117-121, train_clip_from_scratch.py:110) use the CUDA scorer."""
+    from . import metrics_compat
+    ref_metrics_utils_module.calc_scores_given_hparams_vectorized = metrics_compat.calc_scores_given_hparams_vectorized
+    return ref_metrics_utils_module

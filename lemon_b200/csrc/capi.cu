@@ -1,0 +1,55 @@
+// Context management and error plumbing of the C ABI (include/lemon_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <new>
+
+#include "lemon_common.cuh"
+
+int lemon_set_error(lemon_ctx* ctx, int code, const char* fmt, ...) {
+  if (ctx) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+    va_end(ap);
+  }
+  return code;
+}
+
+extern "C" int lemon_version(void) { return 100; }  // 0.1.0
+
+extern "C" int lemon_ctx_create(int device, lemon_ctx** out) {
+  if (!out) return LEMON_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return LEMON_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LEMON_ERR_CUDA;
+  if (prop.major != 10) return LEMON_ERR_UNSUPPORTED;   // sm_100a cubin only: no fallback path exists
+  if (cudaSetDevice(device) != cudaSuccess) return LEMON_ERR_CUDA;
+  lemon_ctx* c = new (std::nothrow) lemon_ctx();
+  if (!c) return LEMON_ERR_INVALID;
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->launches = 0;
+  c->err[0] = 0;
+  c->tc_scratch = nullptr;
+  c->tc_scratch_bytes = 0;
+  c->encode_tiled = nullptr;
+  *out = c;
+  return LEMON_OK;
+}
+
+extern "C" int lemon_ctx_destroy(lemon_ctx* ctx) {
+  if (!ctx) return LEMON_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->tc_scratch) cudaFree(ctx->tc_scratch);
+  delete ctx;
+  return LEMON_OK;
+}
+
+extern "C" const char* lemon_last_error(lemon_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int64_t lemon_launch_count(lemon_ctx* ctx) { return ctx ? ctx->launches : 0; }

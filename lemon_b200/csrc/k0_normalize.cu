@@ -1,0 +1,101 @@
+// K0: row-wise L2 normalisation + fp16 operand copy + rounding-error statistics, and the
+// row-wise cross-modal distance.  HBM-bound: d*4 B read, d*4 + d16*2 B written per row.
+// Restates lib/utils/utils.py:39-40 (F.normalize p=2 dim=1 eps=1e-12) and
+// run_lemon.py:169,173,250-253 (dists_tr, d_1).
+#include "lemon_common.cuh"
+
+namespace lemon {
+
+__device__ __forceinline__ void atomic_max_pos(float* addr, float v) {
+  // non-negative floats order like their bit patterns
+  atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+}
+
+__global__ void __launch_bounds__(256)
+normalize_cast_kernel(const float* __restrict__ in, float* __restrict__ out_f32, __half* __restrict__ out_f16,
+                      float* __restrict__ row_stats, float* __restrict__ stats_max, int64_t n, int d, int d16,
+                      int do_normalize) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const float* x = in + row * d;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { float v = x[c]; ss = fmaf(v, v, ss); }
+    ss = warp_sum(ss);
+    const float denom = do_normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.0f;
+    float sy = 0.f, sh = 0.f, se = 0.f;
+    for (int c = lane; c < d16; c += 32) {
+      float y = 0.f;
+      if (c < d) {
+        y = x[c] / denom;
+        if (out_f32) out_f32[row * d + c] = y;
+      }
+      const __half h = __float2half_rn(y);
+      const float hf = __half2float(h);
+      const float e = y - hf;
+      sy = fmaf(y, y, sy); sh = fmaf(hf, hf, sh); se = fmaf(e, e, se);
+      if (out_f16) out_f16[row * d16 + c] = h;
+    }
+    sy = warp_sum(sy); sh = warp_sum(sh); se = warp_sum(se);
+    const float ny = sqrtf(sy), nh = sqrtf(sh), ne = sqrtf(se);
+    if (lane == 0 && row_stats) {
+      reinterpret_cast<float4*>(row_stats)[row] = make_float4(ny, nh, ne, sy);
+    }
+    m0 = fmaxf(m0, ny); m1 = fmaxf(m1, nh); m2 = fmaxf(m2, ne); m3 = fmaxf(m3, fabsf(sy - 1.0f));
+  }
+  if (stats_max && lane == 0) {
+    atomic_max_pos(stats_max + 0, m0); atomic_max_pos(stats_max + 1, m1);
+    atomic_max_pos(stats_max + 2, m2); atomic_max_pos(stats_max + 3, m3);
+  }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(256)
+rowwise_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                    int64_t n, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    float v = warp_pair_value<METRIC>(a + row * d, b + row * d, d, lane);
+    if (lane == 0) out[row] = (METRIC == LEMON_METRIC_IP) ? 1.0f - v : v;
+  }
+}
+
+}  // namespace lemon
+
+extern "C" int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* out_f16,
+                                    float* row_stats, float* stats_max, int64_t n, int d, int d16,
+                                    int do_normalize, void* stream) {
+  if (!ctx) return LEMON_ERR_INVALID;
+  if (!in || n < 0 || d <= 0) return lemon_set_error(ctx, LEMON_ERR_INVALID, "normalize_cast: bad args");
+  if (out_f16 && (d16 < d || d16 % 64)) return lemon_set_error(ctx, LEMON_ERR_INVALID, "normalize_cast: d16 must be a multiple of 64 and >= d");
+  if (!out_f16) d16 = d;
+  if (n == 0) return LEMON_OK;
+  const int threads = 256;
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = int64_t(ctx->num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  lemon::normalize_cast_kernel<<<unsigned(blocks), threads, 0, (cudaStream_t)stream>>>(
+      in, out_f32, (__half*)out_f16, row_stats, stats_max, n, d, d16, do_normalize);
+  ctx->launches++;
+  LEMON_CUDA_CHECK(ctx, cudaGetLastError());
+  return LEMON_OK;
+}
+
+extern "C" int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* out, int64_t n,
+                                  int d, int metric, void* stream) {
+  if (!ctx) return LEMON_ERR_INVALID;
+  if (!a || !b || !out || n < 0 || d <= 0) return lemon_set_error(ctx, LEMON_ERR_INVALID, "rowwise_dist: bad args");
+  if (n == 0) return LEMON_OK;
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = int64_t(ctx->num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  if (metric == LEMON_METRIC_IP)
+    lemon::rowwise_dist_kernel<LEMON_METRIC_IP><<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, d);
+  else
+    lemon::rowwise_dist_kernel<LEMON_METRIC_L2><<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, d);
+  ctx->launches++;
+  LEMON_CUDA_CHECK(ctx, cudaGetLastError());
+  return LEMON_OK;
+}

@@ -1,0 +1,297 @@
+"""Host-side mirror of the LEMoN scoring path (run_lemon.py:163-176, 235-307 and
+lib/metrics/utils.py:47-82) on top of liblemon_b200.so.
+
+PyTorch is used for device memory, streams and (in dist.py) NCCL plumbing only; all
+arithmetic on the path runs in the hand-written sm_100a kernels behind the C ABI.
+There is no CPU fallback: without a B200 and the built library every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+HP_KEYS = ("beta", "gamma", "tau_1_n", "tau_2_n", "tau_1_m", "tau_2_m")
+KPRIME = 64
+MAX_KP = 64
+MAX_D_TC = 768
+# bound on the fp32 accumulation error of the tensor-core inner product (|q|,|b| <= ~1);
+# validated on the GPU by tests/test_gpu_parity.py::test_tc_error_bound
+ACC_EPS = 3e-5
+METRIC = {"ip": 0, "cosine": 0, "l2": 1, "euclidean": 1}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_dev(x, device, dtype):
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x))
+    if not torch.is_tensor(x):
+        x = torch.as_tensor(x)
+    return x.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+
+
+@dataclass
+class Prepared:
+    """One embedding matrix staged for the kernels: fp32 master (normalised when asked),
+    fp16 tensor-core operand padded to a multiple of 64 columns, rounding statistics."""
+    f32: torch.Tensor          # [n, d]   (d padded to a multiple of 4)
+    f16: torch.Tensor | None   # [n, d16]
+    row_stats: torch.Tensor    # [n, 4]  {||x||, ||x16||, ||x-x16||, ||x||^2}
+    stats_max: torch.Tensor    # [4]     maxima over rows (last: | ||x||^2 - 1 |)
+    n: int
+    d: int
+    d16: int
+
+
+def plan_segments(nq: int, m: int, num_sms: int, cta_group: int) -> int:
+    """Number of DB segments the tensor-core kernel scans independently.  Work items are
+    (row tile, segment); more segments even out the last wave when there are few row
+    tiles, at the price of nseg*64 candidates per row for the re-rank."""
+    units = max(1, num_sms // cta_group)
+    tiles = max(1, -(-nq // (128 * cta_group)))
+    best, best_cost = 1, None
+    for nseg in (1, 2, 3, 4, 6, 8, 12, 16):
+        if nseg > 1 and m // nseg < 4096:
+            break
+        items = tiles * nseg
+        waves = -(-items // units)
+        # time ~ waves * (m / nseg) columns, plus a fixed per-item start-up (~1500 columns' worth)
+        cost = waves * (m / nseg + 1500.0)
+        if best_cost is None or cost < best_cost * 0.97:
+            best, best_cost = nseg, cost
+    return best
+
+
+class LemonScorer:
+    """Drop-in engine for the scoring path.  Mirrors the order of run_lemon.py:
+    ``set_database`` == lines 163-176 (normalise, dists_tr, index.add),
+    ``score``        == lines 235-307 for all queries of a split + utils.py:47-82."""
+
+    def __init__(self, device=None, knn_mode: str = "auto", cta_group: int = 0):
+        if not torch.cuda.is_available():
+            raise _lib.LemonError("lemon_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
+                                   (device if isinstance(device, int) else torch.device(device).index or 0))
+        self.ctx = _lib.get_context(self.device.index)
+        self.lib = self.ctx.lib
+        assert knn_mode in ("auto", "tc", "exact")
+        self.knn_mode = knn_mode
+        self.cta_group = cta_group
+        self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.db = None
+        self.last_info: dict = {}
+
+    # ------------------------------------------------------------------ K0
+    def prepare(self, x, normalize: bool = True, need_f16: bool = True) -> Prepared:
+        x = _to_dev(x, self.device, torch.float32)
+        assert x.dim() == 2
+        n, d = x.shape
+        if d % 4:
+            x = torch.nn.functional.pad(x, (0, 4 - d % 4))
+            d = x.shape[1]
+        d16 = -(-d // 64) * 64
+        out32 = torch.empty_like(x)
+        out16 = torch.empty((n, d16), dtype=torch.float16, device=self.device) if need_f16 else None
+        row_stats = torch.empty((n, 4), dtype=torch.float32, device=self.device)
+        stats_max = torch.zeros(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_normalize_cast(self.ctx.handle, _ptr(x), _ptr(out32), _ptr(out16),
+                                                         _ptr(row_stats), _ptr(stats_max), n, d, d16,
+                                                         int(bool(normalize)), _stream()), "lemon_normalize_cast")
+        return Prepared(out32, out16, row_stats, stats_max, n, d, d16)
+
+    def rowwise_dist(self, a: torch.Tensor, b: torch.Tensor, metric: int) -> torch.Tensor:
+        out = torch.empty(a.shape[0], dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_rowwise_dist(self.ctx.handle, _ptr(a), _ptr(b), _ptr(out), a.shape[0],
+                                                       a.shape[1], metric, _stream()), "lemon_rowwise_dist")
+        return out
+
+    # ------------------------------------------------------------ kNN (a4,a5)
+    def tc_eligible(self, q: Prepared, db: Prepared) -> bool:
+        return (q.f16 is not None and db.f16 is not None and q.d16 == db.d16 and db.d16 <= MAX_D_TC
+                and db.n >= 1 and q.n >= 1)
+
+    def knn_exact(self, q: Prepared, db: Prepared, kp: int, metric: int, top=None, rows=None, n_rows=None):
+        if top is None:
+            top = (torch.empty((q.n, kp), dtype=torch.float32, device=self.device),
+                   torch.empty((q.n, kp), dtype=torch.int32, device=self.device))
+        max_rows = q.n
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_knn_exact(self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(rows), _ptr(n_rows),
+                                                    max_rows, q.n, db.n, db.d, kp, metric, _ptr(top[0]), _ptr(top[1]),
+                                                    _stream()), "lemon_knn_exact")
+        return top
+
+    def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None):
+        cg = self.cta_group if cta_group is None else cta_group
+        if nseg is None:
+            nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 1)
+        cand_val = torch.empty((q.n, nseg * KPRIME), dtype=torch.float32, device=self.device)
+        cand_idx = torch.empty((q.n, nseg * KPRIME), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_knn_candidates(self.ctx.handle, _ptr(q.f16), _ptr(db.f16), q.n, db.n, db.d16,
+                                                         nseg, cg, _ptr(cand_val), _ptr(cand_idx), _stream()),
+                           "lemon_knn_candidates")
+        return cand_val, cand_idx, nseg
+
+    def rerank(self, q: Prepared, db: Prepared, cand_val, cand_idx, nseg: int, kp: int, metric: int,
+               use_bound: bool = True):
+        top_val = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
+        top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
+        uncert = torch.empty(max(q.n, 1), dtype=torch.int32, device=self.device)
+        n_unc = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_rerank(
+                self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(cand_val), _ptr(cand_idx),
+                _ptr(q.row_stats) if use_bound else None, _ptr(db.stats_max) if use_bound else None,
+                C.c_float(ACC_EPS), q.n, db.n, db.d, cand_val.shape[1], nseg, kp, metric, _ptr(top_val), _ptr(top_idx),
+                _ptr(uncert), _ptr(n_unc), _stream()), "lemon_rerank")
+        return top_val, top_idx, uncert, n_unc
+
+    def knn(self, q: Prepared, db: Prepared, kp: int, metric: int, mode: str | None = None):
+        """Exact top-kp lists [nq,kp] (fp32 values, int32 DB rows), total order (best value, lower index).
+        'tc': tensor-core candidates -> fp32 re-rank -> GPU exact fallback for uncertified rows."""
+        mode = mode or self.knn_mode
+        if kp > MAX_KP:
+            raise ValueError(f"k (+1) = {kp} exceeds {MAX_KP}")
+        use_tc = mode == "tc" or (mode == "auto" and self.tc_eligible(q, db))
+        if mode == "tc" and not self.tc_eligible(q, db):
+            raise _lib.LemonError("tensor-core path not eligible for this shape (padded d must be <= 768)")
+        if not use_tc:
+            tv, ti = self.knn_exact(q, db, kp, metric)
+            self.last_info = {"path": "exact"}
+            return tv, ti
+        cand_val, cand_idx, nseg = self.knn_candidates(q, db)
+        top_val, top_idx, uncert, n_unc = self.rerank(q, db, cand_val, cand_idx, nseg, kp, metric)
+        # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the
+        # device, so no host synchronisation is needed here
+        self.knn_exact(q, db, kp, metric, top=(top_val, top_idx), rows=uncert, n_rows=n_unc)
+        self.last_info = {"path": "tc", "nseg": nseg, "n_uncertified": n_unc}
+        return top_val, top_idx
+
+    # ------------------------------------------------- run_lemon.py:163-176
+    def set_database(self, img_db, txt_db, dist_type: str = "cosine", normalize: bool = True,
+                     text_label_ids_db=None):
+        metric = METRIC[dist_type]
+        need16 = self.knn_mode != "exact"
+        xdb = self.prepare(img_db, normalize, need16)
+        ydb = self.prepare(txt_db, normalize, need16)
+        assert xdb.n == ydb.n and xdb.d == ydb.d
+        self.db = {"x": xdb, "y": ydb, "metric": metric, "normalize": normalize,
+                   "dists_tr": self.rowwise_dist(ydb.f32, xdb.f32, metric),
+                   "labels": _to_dev(text_label_ids_db, self.device, torch.int32)}
+        return self
+
+    # ------------------------------- run_lemon.py:235-307 + utils.py:47-82
+    def score(self, img_q, txt_q, *, k: int, query_in_db=None, hparams: dict | None = None,
+              text_label_ids_q=None, return_records: bool = True, queries_are_db: bool = False) -> dict:
+        """Scores every query pair against the database set by ``set_database``.
+
+        query_in_db: None -> val/test rule (search k).  int64[N] (DB row of the query, -1 if
+        absent) -> train rule: search k+1, drop rank 0 if present else the last
+        (run_lemon.py:257-263).  queries_are_db=True reuses the staged DB operands as queries
+        (N == M, the BASELINE 'N x N' configs) instead of staging them twice."""
+        assert self.db is not None, "call set_database first"
+        db = self.db
+        metric = db["metric"]
+        if queries_are_db:
+            xq, yq = db["x"], db["y"]
+        else:
+            need16 = self.knn_mode != "exact"
+            xq = self.prepare(img_q, db["normalize"], need16)
+            yq = self.prepare(txt_q, db["normalize"], need16)
+        nq = xq.n
+        train = query_in_db is not None
+        kp = k + 1 if train else k
+        qid = _to_dev(query_in_db, self.device, torch.int64)
+        lab_q = _to_dev(text_label_ids_q, self.device, torch.int32)
+        lab_db = db["labels"] if lab_q is not None else None
+        if lab_q is not None and lab_db is None:
+            raise ValueError("text_label_ids_q given but the database has no text_label_ids_db")
+        topn = self.knn(xq, db["x"], kp, metric)
+        info_n = self.last_info
+        topm = self.knn(yq, db["y"], kp, metric)
+        info_m = self.last_info
+        dev = self.device
+        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        out = {"d_1": f32(nq)}
+        if return_records:
+            for c in ("D_n", "dists_n", "dists_tr_n", "D_m", "dists_m", "dists_tr_m"):
+                out[c] = f32(nq, k)
+            out["I_n"] = torch.empty((nq, k), dtype=torch.int64, device=dev)
+            out["I_m"] = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        hp_arr = None
+        if hparams is not None:
+            hp_arr = (C.c_double * 6)(*[float(hparams[key]) for key in HP_KEYS])
+            for c in ("s_n", "s_m", "score"):
+                out[c] = torch.empty(nq, dtype=torch.float64, device=dev)
+        g = lambda name: _ptr(out.get(name))
+        with torch.cuda.device(dev):
+            self.ctx.check(self.lib.lemon_score(
+                self.ctx.handle, _ptr(xq.f32), _ptr(yq.f32), _ptr(db["x"].f32), _ptr(db["y"].f32), _ptr(db["dists_tr"]),
+                _ptr(topn[0]), _ptr(topn[1]), _ptr(topm[0]), _ptr(topm[1]), _ptr(qid), _ptr(lab_q), _ptr(lab_db),
+                nq, db["x"].n, db["x"].d, k, kp, metric, hp_arr, g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"),
+                g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"), g("s_n"), g("s_m"), g("score"),
+                _stream()), "lemon_score")
+        self.last_info = {"img": info_n, "txt": info_m}
+        return out
+
+    def combine_scores(self, rec: dict, hparams: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """lib/metrics/utils.py:63-77 on device-resident [N,k] columns."""
+        dev = self.device
+        cols = {c: _to_dev(rec[c], dev, torch.float32) for c in
+                ("D_n", "dists_tr_n", "dists_n", "D_m", "dists_tr_m", "dists_m")}
+        d1 = _to_dev(rec["d_1"], dev, torch.float64)
+        n, k = cols["D_n"].shape
+        sn, sm, sc = (torch.empty(n, dtype=torch.float64, device=dev) for _ in range(3))
+        hp_arr = (C.c_double * 6)(*[float(hparams[key]) for key in HP_KEYS])
+        with torch.cuda.device(dev):
+            self.ctx.check(self.lib.lemon_combine_scores(
+                self.ctx.handle, _ptr(cols["D_n"]), _ptr(cols["dists_tr_n"]), _ptr(cols["dists_n"]), _ptr(cols["D_m"]),
+                _ptr(cols["dists_tr_m"]), _ptr(cols["dists_m"]), _ptr(d1), n, k, hp_arr, _ptr(sn), _ptr(sm), _ptr(sc),
+                _stream()), "lemon_combine_scores")
+        return sc, sn, sm
+
+
+_default_scorers: dict = {}
+
+
+def get_scorer(device=None, knn_mode: str = "auto") -> LemonScorer:
+    key = (str(device), knn_mode)
+    if key not in _default_scorers:
+        _default_scorers[key] = LemonScorer(device, knn_mode)
+    return _default_scorers[key]
+
+
+def score_pairs(img_q, txt_q, img_db=None, txt_db=None, *, k: int, dist_type: str = "cosine",
+                query_in_db=None, hparams: dict | None = None, text_label_ids_q=None, text_label_ids_db=None,
+                normalize: bool = True, return_records: bool = True, to_host: bool = False, device=None,
+                knn_mode: str = "auto") -> dict:
+    """Fused replacement of run_lemon.py:163-314 + :406-407 in one call (SURVEY.md §8b seam 3).
+
+    img_db/txt_db None means DB == queries (N == M).  Returns the df columns of
+    run_lemon.py:291-307 as tensors: d_1 [N]; D_n, dists_n, dists_tr_n, D_m, dists_m, dists_tr_m
+    [N,k] fp32; I_n, I_m [N,k] int64; and, with hparams, s_n, s_m, score [N] float64."""
+    sc = get_scorer(device, knn_mode)
+    same = img_db is None
+    sc.set_database(img_q if same else img_db, txt_q if same else txt_db, dist_type, normalize, text_label_ids_db
+                    if not same or text_label_ids_db is not None else text_label_ids_q)
+    out = sc.score(img_q, txt_q, k=k, query_in_db=query_in_db, hparams=hparams, text_label_ids_q=text_label_ids_q,
+                   return_records=return_records, queries_are_db=same)
+    if to_host:
+        out = {name: t.cpu().numpy() for name, t in out.items()}
+    return out

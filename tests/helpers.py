@@ -38,3 +38,56 @@ def iid_pairs(n, d, seed=0):
     x = rng.standard_normal((n, d)); x /= np.linalg.norm(x, axis=1, keepdims=True)
     y = rng.standard_normal((n, d)); y /= np.linalg.norm(y, axis=1, keepdims=True)
     return x.astype(np.float32), y.astype(np.float32)
+
+
+def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_in_db=None, hparams=None,
+                         lab_q=None, lab_db=None, eps_tie=None, rtol=1e-5, normalize=True):
+    """Acceptance check of SURVEY.md §8c for a score_pairs() result `out` (numpy arrays):
+    neighbour SETS equal the float64 oracle's modulo eps-ties at the boundary; record arrays and
+    scores within `rtol` of the oracle — rows whose sets differ by an excused tie are compared
+    with the oracle re-evaluated on the returned index sets.  Returns counts."""
+    from oracle import lemon_oracle as O
+    metric = "ip" if dist_type == "cosine" else "l2"
+    if eps_tie is None:
+        eps_tie = O.EPS_TIE_COSINE * (1 if metric == "ip" else 2)
+    if normalize:
+        xq, yq, xdb, ydb = (O.normalize_vectors(a) for a in (xq, yq, xdb, ydb))
+    ref = O.lemon_oracle(xq, yq, xdb, ydb, k=k, dist_type=dist_type, query_in_db=query_in_db, hparams=hparams,
+                         normalize=False, text_label_ids_q=lab_q, text_label_ids_db=lab_db)
+    N = xq.shape[0]
+    stats = {}
+    tie_rows = np.zeros(N, bool)
+    for side, q, db in (("n", xq, xdb), ("m", yq, ydb)):
+        I_got = out[f"I_{side}"]
+        assert I_got.shape == (N, k) and I_got.dtype == np.int64
+        # kNN acceptance is defined on the searched list (k or k+1); with self-exclusion compare the kept k
+        D_ref = O.pair_values(q, db, ref[f"I_{side}"], metric)
+        # boundary value: the worst kept neighbour of the oracle
+        r = O.compare_neighbor_sets(q, db, I_got, k, metric, eps_tie=eps_tie, D_ref=D_ref, I_ref=ref[f"I_{side}"])
+        assert r["wrong"] == 0, f"side {side}: {r['wrong']} rows with wrong neighbour sets, e.g. {r['wrong_rows'][:5]}"
+        stats[f"exact_{side}"], stats[f"tie_excused_{side}"] = r["exact"], r["tie_excused"]
+        tie_rows[r["excused_rows"]] = True
+    # rows with tie-excused sets: oracle re-evaluated on the returned sets
+    ref2 = O.lemon_oracle(xq, yq, xdb, ydb, k=k, dist_type=dist_type, hparams=hparams, normalize=False,
+                          text_label_ids_q=lab_q, text_label_ids_db=lab_db, given_I=(out["I_n"], out["I_m"]))
+    if query_in_db is not None:
+        pass  # given_I lists are already self-excluded
+    cols = ("D_n", "dists_n", "dists_tr_n", "D_m", "dists_m", "dists_tr_m")
+    for c in cols:
+        side = c[-1]
+        # align by neighbour id (near-ties may permute the order inside a row)
+        og = np.argsort(out[f"I_{side}"], axis=1, kind="stable")
+        orf = np.argsort(ref[f"I_{side}"], axis=1, kind="stable")
+        a = np.take_along_axis(out[c].astype(np.float64), og, axis=1)
+        b = np.take_along_axis(ref[c], orf, axis=1)
+        ok = ~tie_rows
+        np.testing.assert_allclose(a[ok], b[ok], rtol=rtol, atol=2e-6, err_msg=c)
+        np.testing.assert_allclose(out[c][tie_rows].astype(np.float64), ref2[c][tie_rows], rtol=rtol, atol=2e-6,
+                                   err_msg=c + " (tie rows)")
+    np.testing.assert_allclose(out["d_1"], ref["d_1"], rtol=rtol, atol=2e-6)
+    if hparams is not None:
+        for c in ("s_n", "s_m", "score"):
+            np.testing.assert_allclose(out[c][~tie_rows], ref[c][~tie_rows], rtol=rtol, atol=1e-6, err_msg=c)
+            np.testing.assert_allclose(out[c][tie_rows], ref2[c][tie_rows], rtol=rtol, atol=1e-6, err_msg=c + " (tie rows)")
+    stats["tie_rows"] = int(tie_rows.sum())
+    return stats

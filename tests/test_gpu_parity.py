@@ -1,0 +1,160 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Every call goes through the C ABI of
+liblemon_b200.so; the oracle is only the checker."""
+import os
+
+import numpy as np
+import pytest
+
+from tests.helpers import clustered_pairs, iid_pairs, check_against_oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+HP = {"beta": 5.0, "gamma": 5.0, "tau_1_n": 0.1, "tau_2_n": 5.0, "tau_1_m": 0.1, "tau_2_m": 5.0}
+COLS = ("D_n", "D_m", "dists_tr_n", "dists_tr_m", "dists_n", "dists_m")
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import torch
+    import lemon_b200
+    assert torch.cuda.is_available()
+    assert os.path.exists(lemon_b200.LIB_PATH), "liblemon_b200.so must be built in-tree"
+    return lemon_b200
+
+
+def _np(out):
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def test_normalize_matches_reference_golden(lb):
+    g = np.load(os.path.join(GOLD, "normalize.npz"))
+    sc = lb.get_scorer()
+    p = sc.prepare(g["x"], normalize=True)
+    y = p.f32.cpu().numpy()
+    np.testing.assert_allclose(y, g["y"], rtol=5e-7, atol=1e-30)
+    assert (y[3] == 0).all()
+    # fp16 operand copy + statistics
+    y16 = p.f16.cpu().numpy()[:, : y.shape[1]]
+    assert (y16 == y.astype(np.float16)).all()
+    st = p.row_stats.cpu().numpy()
+    np.testing.assert_allclose(st[:, 2], np.linalg.norm(y - y16.astype(np.float32), axis=1), rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(st[:, 0], np.linalg.norm(y, axis=1), rtol=1e-5)
+
+
+@pytest.mark.parametrize("tag", ["k30", "k5", "k1"])
+def test_combine_scores_matches_reference_golden(lb, tag):
+    import pandas as pd
+    from lemon_b200 import metrics_compat
+    g = np.load(os.path.join(GOLD, f"scores_{tag}.npz"))
+    n = len(g["d_1"])
+    df = pd.DataFrame([{**{c: g[c][i] for c in COLS}, "d_1": float(g["d_1"][i])} for i in range(n)])
+    for h, row in enumerate(g["hparams"]):
+        hp = dict(zip(lb.HP_KEYS, (float(v) for v in row)))
+        s, dn, dm = metrics_compat.calc_scores_given_hparams_vectorized(df, hp, return_dn=True)
+        assert isinstance(s, np.ndarray) and s.dtype == np.float64 and s.shape == (n,)
+        np.testing.assert_allclose(s, g[f"vec_scores_{h}"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dn, g[f"vec_dn_{h}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(dm, g[f"vec_dm_{h}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(s, g[f"loop_scores_{h}"], rtol=1e-5, atol=1e-6)
+        s2 = metrics_compat.calc_scores_given_hparams_vectorized(df, hp)
+        assert (s2 == s).all()
+
+
+@pytest.mark.parametrize("d,k", [(64, 1), (96, 5), (512, 30), (768, 50), (50, 7)])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_knn_exact_kernel_vs_oracle(lb, d, k, metric):
+    from oracle import lemon_oracle as O
+    x, _ = iid_pairs(1500, d, seed=d + k)
+    q = x[:333] + 0.05 * iid_pairs(333, d, seed=7)[0]
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(q, normalize=False), sc.prepare(x, normalize=False)
+    tv, ti = sc.knn(qp, dbp, k, 0 if metric == "ip" else 1, mode="exact")
+    tv, ti = tv.cpu().numpy(), ti.cpu().numpy().astype(np.int64)
+    D, I = O.knn_search(q, x, k, metric)
+    r = O.compare_neighbor_sets(q, x, ti, k, metric, eps_tie=4e-6, D_ref=D, I_ref=I)
+    assert r["wrong"] == 0
+    assert r["exact"] >= 0.99 * r["rows"]
+    same = (ti == I).all(axis=1)
+    np.testing.assert_allclose(tv[same], D[same], rtol=1e-5, atol=2e-6)
+    # sortedness (best first)
+    assert ((np.diff(tv, axis=1) <= 0) if metric == "ip" else (np.diff(tv, axis=1) >= 0)).all()
+
+
+def test_knn_exact_ties_resolve_by_index(lb):
+    from oracle import lemon_oracle as O
+    base, _ = iid_pairs(40, 64, seed=11)
+    db = np.repeat(base, 25, axis=0)            # 1000 rows, every vector 25 times
+    perm = np.random.RandomState(0).permutation(len(db))
+    db = db[perm]
+    q = base[:16]
+    sc = lb.get_scorer()
+    tv, ti = sc.knn(sc.prepare(q, False), sc.prepare(db, False), 31, 0, mode="exact")
+    D, I = O.knn_search(q, db, 31, "ip")
+    assert (ti.cpu().numpy() == I).all()        # exact duplicates: identical order, ascending DB index
+
+
+def test_knn_exact_small_db_pads_like_faiss(lb):
+    x, _ = iid_pairs(5, 64, seed=3)
+    sc = lb.get_scorer()
+    tv, ti = sc.knn(sc.prepare(x, False), sc.prepare(x[:3], False), 6, 0, mode="exact")
+    ti, tv = ti.cpu().numpy(), tv.cpu().numpy()
+    assert (ti[:, 3:] == -1).all() and np.isneginf(tv[:, 3:]).all() and (ti[:, :3] >= 0).all()
+
+
+@pytest.mark.parametrize("dist_type", ["cosine", "euclidean"])
+@pytest.mark.parametrize("train", [True, False])
+def test_score_pairs_exact_mode_vs_oracle(lb, dist_type, train):
+    x, y, _, _ = clustered_pairs(1200, 128, n_clusters=24, seed=21, noise_frac=0.3)
+    k = 10
+    raw = lambda a: (a * np.random.RandomState(5).uniform(0.5, 3.0, (a.shape[0], 1))).astype(np.float32)
+    xr, yr = raw(x), raw(y)                      # un-normalised inputs: exercises K0
+    if train:
+        out = _np(lb.score_pairs(xr, yr, k=k, dist_type=dist_type, query_in_db=np.arange(1200), hparams=HP,
+                                 knn_mode="exact"))
+        st = check_against_oracle(out, xr, yr, xr, yr, k=k, dist_type=dist_type, query_in_db=np.arange(1200), hparams=HP)
+        assert not (out["I_n"] == np.arange(1200)[:, None]).any()
+    else:
+        out = _np(lb.score_pairs(xr[:300], yr[:300], xr[300:], yr[300:], k=k, dist_type=dist_type, hparams=HP,
+                                 knn_mode="exact"))
+        st = check_against_oracle(out, xr[:300], yr[:300], xr[300:], yr[300:], k=k, dist_type=dist_type, hparams=HP)
+    assert st["exact_n"] + st["tie_excused_n"] == out["I_n"].shape[0]
+
+
+def test_score_pairs_query_not_in_db_drops_last(lb):
+    x, y, _, _ = clustered_pairs(600, 64, n_clusters=12, seed=22)
+    qid = np.arange(600)
+    qid[::3] = -1                                 # a third of the train queries were not sampled into the DB
+    out = _np(lb.score_pairs(x, y, x, y, k=6, query_in_db=qid, hparams=HP, knn_mode="exact"))
+    check_against_oracle(out, x, y, x, y, k=6, query_in_db=qid, hparams=HP)
+    # rows with qid == -1 keep rank 0 (the sample itself, since it IS physically in this DB)
+    assert (out["I_n"][::3, 0] == np.arange(600)[::3]).all()
+
+
+def test_score_pairs_discrete_text_metric(lb):
+    x, y, lab, _ = clustered_pairs(900, 64, n_clusters=20, seed=23, dup_text_classes=10)
+    out = _np(lb.score_pairs(x, y, k=8, query_in_db=np.arange(900), hparams=HP, text_label_ids_q=lab,
+                             text_label_ids_db=lab, knn_mode="exact"))
+    check_against_oracle(out, x, y, x, y, k=8, query_in_db=np.arange(900), hparams=HP, lab_q=lab, lab_db=lab)
+    assert (out["D_n"] > 0).any() and set(np.unique(out["dists_n"])) <= {0.0, 1.0}
+
+
+def test_faiss_compat_api(lb):
+    from lemon_b200 import faiss_compat as faiss
+    from oracle import lemon_oracle as O
+    x, _ = iid_pairs(700, 96, seed=31)
+    q = x[:50] * 1.7
+    for cls, metric in ((faiss.IndexFlatIP, "ip"), (faiss.IndexFlatL2, "l2")):
+        index = cls(96)
+        index.add(x[:400]); index.add(x[400:])
+        assert index.ntotal == 700
+        D, I = index.search(q, 9)
+        assert isinstance(D, np.ndarray) and D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (50, 9)
+        Dr, Ir = O.knn_search(q, x, 9, metric)
+        r = O.compare_neighbor_sets(q, x, I, 9, metric, eps_tie=4e-6, D_ref=Dr, I_ref=Ir)
+        assert r["wrong"] == 0
+        np.testing.assert_allclose(D[(I == Ir).all(1)], Dr[(I == Ir).all(1)], rtol=1e-5, atol=3e-6)
+    small = faiss.IndexFlatIP(96); small.add(x[:4])
+    D, I = small.search(q[:2], 6)
+    assert (I[:, 4:] == -1).all() and np.isneginf(D[:, 4:]).all()
+    with pytest.raises(RuntimeError):
+        small.add(x[:, :50])

@@ -1,6 +1,500 @@
+// K1: tensor-core candidate search.  Replaces faiss IndexFlatIP.search (run_lemon.py:235-236)
+// for the bulk of the work: S = Q * DB^T on tcgen05 (fp16 operands, fp32 TMEM accumulators) with a
+// streaming top-64 fused into the epilogue, so the nq x m similarity matrix never reaches HBM.
+//
+// Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
+//   warp 0   TMA producer : query tile (resident in SMEM for the whole DB scan) + DB tiles (ring)
+//   warp 1   MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
+//                            double-buffered in TMEM (2 x BN columns)
+//   warp 2   TMEM alloc / dealloc
+//   warps 4-7 epilogue    : tcgen05.ld 32x32b (thread == query row), threshold filter in registers,
+//                            survivors appended to a per-row 256-entry buffer (L2-resident global
+//                            scratch), warp-wide bitonic compaction to the best 64 when it fills.
+// Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
+// in the same order and DB tiles are served from L2.
+#include <cuda.h>
+
 #include "lemon_common.cuh"
+
+namespace lemon {
+
+constexpr int kTcThreads = 256;
+constexpr int kBM = 128;                       // query rows per CTA (TMEM lanes)
+constexpr int kBK = 64;                        // K elements per smem chunk: 128 B rows, SWIZZLE_128B
+constexpr int kAChunkBytes = kBM * kBK * 2;    // 16 KB
+constexpr int kMaxSmem = 232448;               // 227 KB
+
+struct TcParams {
+  int64_t nq, m;
+  int kchunks;          // d16 / 64
+  int nseg;
+  int64_t seg_len;      // columns per segment (multiple of BN)
+  int nstage;
+  int64_t n_items;      // row_tiles * nseg
+  float* cand_val;
+  int32_t* cand_idx;
+  uint64_t* scratch;    // [gridDim.x][128][kCap]
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(local_addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (true) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (clock64() - t0 > 8000000000ll) __trap();   // ~4 s: fail loudly instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    // executed by both CTAs of the pair; `bar` is the shared::cluster address of the LEADER's barrier
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (CG == 1) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// tcgen05.commit: the mbarrier is arrived on when all MMAs issued so far by this thread are done.
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;   // same barrier offset in both CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B, 8-row groups 1024 B apart)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+
+// ---------------------------------------------------------------- streaming top-k (epilogue)
+// Compacts the buffers of all lanes whose count passed `limit`: the warp sorts that lane's 256-slot
+// buffer, keeps the best 64 and raises the lane's threshold to the 64th value.
+__device__ __forceinline__ void compact_rows(uint64_t* warp_buf, int& cnt, float& theta, int limit, int lane) {
+  unsigned need = __ballot_sync(kFull, cnt > limit);
+  while (need) {
+    const int L = __ffs(need) - 1;
+    need &= need - 1;
+    const int cntL = __shfl_sync(kFull, cnt, L);
+    uint64_t* b = warp_buf + size_t(L) * kCap;
+    uint64_t key[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
+      key[i] = (lane * 8 + i) < cntL ? t.x : 0ull;
+      key[i + 1] = (lane * 8 + i + 1) < cntL ? t.y : 0ull;
+    }
+    warp_sort256_desc(key, lane);
+    if (lane < kKeep / 8) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2)
+        *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
+    }
+    const uint64_t k64 = shfl_u64(key[7], kKeep / 8 - 1);
+    if (lane == L) {
+      if (cntL >= kKeep) { theta = key_val(k64); cnt = kKeep; }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------ kernel
+template <int CG, int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
+  const int64_t unit = blockIdx.x / CG;            // CTA (pair) id
+  const int64_t n_units = gridDim.x / CG;
+  constexpr int kBRows = BN / CG;                  // DB rows this CTA stages per tile
+  constexpr uint32_t kStageBytes = kBRows * kBK * 2;
+  constexpr uint32_t kTmemCols = 2 * BN;
+
+  const uint32_t a_smem = smem_base;
+  const uint32_t b_smem = a_smem + uint32_t(p.kchunks) * kAChunkBytes;
+  const uint32_t bar_base = b_smem + uint32_t(p.nstage) * kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (p.nstage + s); };
+  const uint32_t a_full = bar_base + 8u * (2 * p.nstage);
+  const uint32_t a_empty = a_full + 8;
+  const uint32_t tmem_full = a_full + 16;    // [2]
+  const uint32_t tmem_empty = a_full + 32;   // [2]
+  const uint32_t tmem_slot = a_full + 48;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<CG>(tmem_slot, kTmemCols);
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int64_t n_row_tiles = p.n_items / p.nseg;
+  (void)n_row_tiles;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      const uint32_t full0 = (CG == 2) ? mapa_rank0(full_bar(0)) : full_bar(0);   // leader's barriers
+      const uint32_t afull_l = (CG == 2) ? mapa_rank0(a_full) : a_full;
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
+        const int64_t rt = item / p.nseg, seg = item % p.nseg;
+        const int64_t col0 = seg * p.seg_len;
+        const int64_t col1 = min(p.m, col0 + p.seg_len);
+        const int64_t ntiles = col1 > col0 ? (col1 - col0 + BN - 1) / BN : 0;
+        if (ntiles == 0) { --it; continue; }
+        const int row0 = int(rt * (kBM * CG) + cta_rank * kBM);
+        // query tile: wait until the previous item's MMAs have drained it
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        if (cta_rank == 0) mbar_arrive_expect_tx(a_full, uint32_t(p.kchunks) * kAChunkBytes * CG);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d<CG>(a_smem + kc * kAChunkBytes, &map_q, afull_l, kc * kBK, row0);
+        for (int64_t t = 0; t < ntiles; ++t) {
+          const int dbrow = int(col0 + t * BN + cta_rank * kBRows);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), kStageBytes * CG);
+            tma_load_2d<CG>(b_smem + stage * kStageBytes, &map_db, full0 + 8u * stage, kc * kBK, dbrow);
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((kBM * CG) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; uint32_t it = 0; uint32_t tc = 0;
+      for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
+        const int64_t seg = item % p.nseg;
+        const int64_t col0 = seg * p.seg_len;
+        const int64_t col1 = min(p.m, col0 + p.seg_len);
+        const int64_t ntiles = col1 > col0 ? (col1 - col0 + BN - 1) / BN : 0;
+        if (ntiles == 0) { --it; continue; }
+        mbar_wait(a_full, it & 1);
+        tc_fence_after();
+        for (int64_t t = 0; t < ntiles; ++t, ++tc) {
+          const uint32_t buf = tc & 1, use = tc >> 1;
+          mbar_wait(tmem_empty + 8 * buf, (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * BN;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint64_t adesc = make_smem_desc(a_smem + kc * kAChunkBytes);
+            const uint64_t bdesc = make_smem_desc(b_smem + stage * kStageBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < kBK / 16; ++k4)   // +32 B per UMMA_K inside the 128 B swizzle row
+              umma_f16<CG>(d_tmem, adesc + uint64_t(2 * k4), bdesc + uint64_t(2 * k4), idesc, (kc | k4) != 0);
+            umma_commit<CG>(empty_bar(stage));       // frees the DB stage (both CTAs)
+            if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+          }
+          umma_commit<CG>(tmem_full + 8 * buf);      // accumulator ready (both CTAs)
+        }
+        umma_commit<CG>(a_empty);                    // query tile drained (both CTAs)
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== epilogue: streaming top-64 ===============================
+    const int quad = warp & 3;
+    const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
+    uint64_t* warp_buf = p.scratch + (size_t(blockIdx.x) * kBM + size_t(quad) * 32) * kCap;
+    uint64_t* my_buf = warp_buf + size_t(lane) * kCap;
+    const uint32_t tempty0 = (CG == 2) ? mapa_rank0(tmem_empty) : tmem_empty;
+    uint32_t tc = 0;
+    for (int64_t item = unit; item < p.n_items; item += n_units) {
+      const int64_t rt = item / p.nseg, seg = item % p.nseg;
+      const int64_t col0 = seg * p.seg_len;
+      const int64_t col1 = min(p.m, col0 + p.seg_len);
+      const int64_t ntiles = col1 > col0 ? (col1 - col0 + BN - 1) / BN : 0;
+      const int64_t row = rt * (kBM * CG) + cta_rank * kBM + quad * 32 + lane;
+      float theta = -CUDART_INF_F;
+      int cnt = 0;
+      for (int64_t t = 0; t < ntiles; ++t, ++tc) {
+        const uint32_t buf = tc & 1, use = tc >> 1;
+        mbar_wait(tmem_full + 8 * buf, use & 1);
+        tc_fence_after();
+        const int64_t colb = col0 + t * BN;
+        const int valid = int(min(int64_t(BN), col1 - colb));
+        const uint32_t taddr = tmem_base + tmem_lane + buf * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (c >= valid) break;
+          float v[32];
+          tmem_ld32(taddr + c, v);
+          if (c + 32 > valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (c + j >= valid) v[j] = -CUDART_INF_F;
+          }
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          if (mx > theta) {
+            const uint32_t idx0 = uint32_t(colb + c);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] > theta) { my_buf[cnt] = make_key(v[j], idx0 + j); ++cnt; }
+            }
+          }
+          __syncwarp();
+          if (__any_sync(kFull, cnt > kCap - 32)) compact_rows(warp_buf, cnt, theta, kCap - 32, lane);
+        }
+        // hand the accumulator buffer back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
+        }
+      }
+      // item done: sort every row's buffer and emit its best 64 (descending; ties by lower index)
+      __syncwarp();
+      for (int L = 0; L < 32; ++L) {
+        const int cntL = __shfl_sync(kFull, cnt, L);
+        const int64_t rowL = __shfl_sync(kFull, row, L);
+        uint64_t* b = warp_buf + size_t(L) * kCap;
+        uint64_t key[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
+          key[i] = (lane * 8 + i) < cntL ? tt.x : 0ull;
+          key[i + 1] = (lane * 8 + i + 1) < cntL ? tt.y : 0ull;
+        }
+        warp_sort256_desc(key, lane);
+        if (rowL < p.nq && lane < kKeep / 8) {
+          float* ov = p.cand_val + (rowL * p.nseg + seg) * kKeep + lane * 8;
+          int32_t* oi = p.cand_idx + (rowL * p.nseg + seg) * kKeep + lane * 8;
+          float fv[8]; int32_t iv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const bool ok = key[i] != 0ull;
+            fv[i] = ok ? key_val(key[i]) : -CUDART_INF_F;
+            iv[i] = ok ? key_idx(key[i]) : -1;
+          }
+          *reinterpret_cast<float4*>(ov) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+          *reinterpret_cast<float4*>(ov + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+          *reinterpret_cast<int4*>(oi) = make_int4(iv[0], iv[1], iv[2], iv[3]);
+          *reinterpret_cast<int4*>(oi + 4) = make_int4(iv[4], iv[5], iv[6], iv[7]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  // =============================== teardown ===============================
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(lemon_ctx* ctx, CUtensorMap* map, const void* base, int64_t rows, int d16, int box_rows) {
+  if (!ctx->encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+      return lemon_set_error(ctx, LEMON_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    ctx->encode_tiled = fn;
+  }
+  const cuuint64_t gdim[2] = {cuuint64_t(d16), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(d16) * 2};
+  const cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+      map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return lemon_set_error(ctx, LEMON_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
+  return LEMON_OK;
+}
+
+template <int CG, int BN>
+static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg,
+                     float* cand_val, int32_t* cand_idx, cudaStream_t stream) {
+  const int kchunks = d16 / kBK;
+  const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
+  const uint32_t stage_bytes = (BN / CG) * kBK * 2;
+  const int64_t avail = int64_t(kMaxSmem) - 1024 /*align*/ - 256 /*barriers*/ - a_bytes;
+  int nstage = int(avail / stage_bytes);
+  if (nstage > 8) nstage = 8;
+  if (nstage < 2) return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: d16=%d leaves no room for a DB ring", d16);
+  const size_t smem = 1024 + a_bytes + size_t(nstage) * stage_bytes + 256;
+
+  TcParams p;
+  p.nq = nq; p.m = m; p.kchunks = kchunks; p.nstage = nstage;
+  int64_t seg_len = (m + nseg - 1) / nseg;
+  seg_len = (seg_len + BN - 1) / BN * BN;
+  // segments past the end of the DB are legal: they emit empty (-inf, -1) lists
+  p.nseg = nseg; p.seg_len = seg_len;
+  const int64_t row_tiles = (nq + kBM * CG - 1) / (kBM * CG);
+  p.n_items = row_tiles * nseg;
+  p.cand_val = cand_val; p.cand_idx = cand_idx;
+
+  int64_t units = ctx->num_sms / CG;
+  if (units > p.n_items) units = p.n_items;
+  const unsigned grid = unsigned(units * CG);
+  const size_t need = size_t(grid) * kBM * kCap * sizeof(uint64_t);
+  if (ctx->tc_scratch_bytes < need) {
+    if (ctx->tc_scratch) LEMON_CUDA_CHECK(ctx, cudaFree(ctx->tc_scratch));
+    ctx->tc_scratch = nullptr; ctx->tc_scratch_bytes = 0;
+    LEMON_CUDA_CHECK(ctx, cudaMalloc(&ctx->tc_scratch, size_t(ctx->num_sms) * kBM * kCap * sizeof(uint64_t)));
+    ctx->tc_scratch_bytes = size_t(ctx->num_sms) * kBM * kCap * sizeof(uint64_t);
+  }
+  p.scratch = reinterpret_cast<uint64_t*>(ctx->tc_scratch);
+
+  CUtensorMap map_q, map_db;
+  int rc = make_map(ctx, &map_q, q16, nq, d16, kBM);
+  if (rc) return rc;
+  rc = make_map(ctx, &map_db, db16, m, d16, BN / CG);
+  if (rc) return rc;
+
+  auto kern = knn_tc_kernel<CG, BN>;
+  LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  LEMON_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, map_q, map_db, p));
+  ctx->launches++;
+  return LEMON_OK;
+}
+
+}  // namespace lemon
+
 extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
                                     int d16, int nseg, int cta_group, float* cand_val, int32_t* cand_idx,
                                     void* stream) {
-  return lemon_set_error(ctx, LEMON_ERR_UNSUPPORTED, "tensor-core kernel not built yet");
+  using namespace lemon;
+  if (!ctx) return LEMON_ERR_INVALID;
+  if (!q16 || !db16 || !cand_val || !cand_idx || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
+      nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands)", LEMON_MAX_D_TC);
+  if (nq == 0) return LEMON_OK;
+  if (cta_group == 0) cta_group = 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  LEMON_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  if (cta_group == 1) {
+    if (d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+  }
+  if (cta_group == 2) return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+  return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: cta_group must be 0, 1 or 2");
 }

@@ -281,11 +281,14 @@ def pair_values(q, db, I, metric: str) -> np.ndarray:
 
 # ------------------------------------------------------------- acceptance rule
 def compare_neighbor_sets(q, db, I_got: np.ndarray, k: int, metric: str = "ip",
-                          eps_tie: float = EPS_TIE_COSINE, D_ref=None, I_ref=None) -> dict:
+                          eps_tie: float = EPS_TIE_COSINE, D_ref=None, I_ref=None, top_boundary=None) -> dict:
     """SURVEY.md §8c acceptance: per row the returned index SET must equal the
     float64 oracle's, except members whose float64 value lies within ``eps_tie`` of
-    the oracle's k-th value (eps-ties at the boundary).  Returns counts and the rows
-    that were tie-excused / wrong."""
+    the oracle's k-th value (eps-ties at the boundary).  top_boundary [N] (NaN = none):
+    value of the rank-0 entry the train-split rule dropped (run_lemon.py:257-263 drops
+    rank 0 without checking that it IS the sample, so with duplicate rows which of the
+    tied entries goes is a tie at that second boundary as well).  Returns counts and the
+    rows that were tie-excused / wrong."""
     if I_ref is None:
         D_ref, I_ref = knn_search(q, db, k, metric)
     got_vals = pair_values(q, db, np.where(I_got < 0, 0, I_got), metric)
@@ -300,10 +303,14 @@ def compare_neighbor_sets(q, db, I_got: np.ndarray, k: int, metric: str = "ip",
         if sg == sr:
             exact += 1
             continue
+        bounds = [kth[r]]
+        if top_boundary is not None and np.isfinite(top_boundary[r]):
+            bounds.append(top_boundary[r])
+        near = lambda v: any(abs(v - b) <= eps_tie for b in bounds)
         extra = [j for j, i in enumerate(I_got[r]) if i not in sr]
-        ok = all(abs(got_vals[r, j] - kth[r]) <= eps_tie for j in extra)
+        ok = all(near(got_vals[r, j]) for j in extra)
         miss = [j for j, i in enumerate(I_ref[r]) if i not in sg]
-        ok = ok and all(abs(D_ref[r, j] - kth[r]) <= eps_tie for j in miss)
+        ok = ok and all(near(D_ref[r, j]) for j in miss)
         if ok:
             excused += 1
             excused_rows.append(r)

@@ -63,7 +63,12 @@ def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_
         # kNN acceptance is defined on the searched list (k or k+1); with self-exclusion compare the kept k
         D_ref = O.pair_values(q, db, ref[f"I_{side}"], metric)
         # boundary value: the worst kept neighbour of the oracle
-        r = O.compare_neighbor_sets(q, db, I_got, k, metric, eps_tie=eps_tie, D_ref=D_ref, I_ref=ref[f"I_{side}"])
+        top = None
+        if query_in_db is not None:   # value of the dropped rank-0 entry for rows that are in the DB
+            raw_D = ref["raw"][0 if side == "n" else 2]
+            top = np.where(np.asarray(query_in_db) >= 0, raw_D[:, 0], np.nan)
+        r = O.compare_neighbor_sets(q, db, I_got, k, metric, eps_tie=eps_tie, D_ref=D_ref, I_ref=ref[f"I_{side}"],
+                                    top_boundary=top)
         assert r["wrong"] == 0, f"side {side}: {r['wrong']} rows with wrong neighbour sets, e.g. {r['wrong_rows'][:5]}"
         stats[f"exact_{side}"], stats[f"tie_excused_{side}"] = r["exact"], r["tie_excused"]
         tie_rows[r["excused_rows"]] = True

@@ -1,0 +1,45 @@
+"""Debug driver for the tensor-core candidate kernel: compares lemon_knn_candidates with a torch fp32
+matmul of the same fp16-rounded operands.  usage: python tools/tc_debug.py CG NQ M D [NSEG]"""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import lemon_b200
+from tests.helpers import iid_pairs, clustered_pairs
+
+cg, nq, m, d = (int(a) for a in sys.argv[1:5])
+nseg = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+sc = lemon_b200.get_scorer()
+x, _, _, _ = clustered_pairs(m, d, n_clusters=max(4, m // 100), seed=1)
+q = x[:nq].copy() if nq <= m else iid_pairs(nq, d, seed=2)[0]
+qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
+torch.cuda.synchronize()
+t0 = time.time()
+cv, ci, nseg = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+torch.cuda.synchronize()
+print(f"cg={cg} nq={nq} m={m} d={d} nseg={nseg}: kernel returned in {time.time()-t0:.3f}s")
+S = qp.f16.float() @ dbp.f16.float().T
+cv_h, ci_h = cv.cpu().numpy(), ci.cpu().numpy()
+# merge segments -> top 64 overall
+order = np.argsort(-cv_h, axis=1, kind="stable")[:, :64]
+mv = np.take_along_axis(cv_h, order, 1); mi = np.take_along_axis(ci_h, order, 1)
+tv, ti = torch.topk(S, min(64, m), dim=1)
+tv, ti = tv.cpu().numpy(), ti.cpu().numpy()
+kk = tv.shape[1]
+print("max |val diff| top-%d:" % kk, np.abs(mv[:, :kk] - tv).max())
+same = np.array([len(set(a[:kk]) & set(b)) for a, b in zip(mi, ti)])
+print("set overlap min/mean:", same.min(), same.mean(), " rows fully equal:", (same == kk).mean())
+# gathered check: value reported for idx equals S[row, idx]
+g = np.take_along_axis(S.cpu().numpy(), np.where(mi[:, :kk] < 0, 0, mi[:, :kk]), 1)
+print("max |reported - S[idx]|:", np.abs(g - mv[:, :kk]).max(), " any idx<0:", (mi[:, :kk] < 0).any(), " idx>=m:", (mi >= m).any())
+# per-segment lists sorted descending?
+seg = cv_h.reshape(nq, nseg, 64)
+print("segments sorted desc:", bool((np.diff(seg, axis=2) <= 0).all()))
+if "--time" in sys.argv:
+    for _ in range(3): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"time {ms:.3f} ms  -> {2.0*nq*m*dbp.d16/ms/1e9:.1f} TFLOP/s")

@@ -488,7 +488,7 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
       nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands)", LEMON_MAX_D_TC);
   if (nq == 0) return LEMON_OK;
-  if (cta_group == 0) cta_group = 1;
+  if (cta_group == 0) cta_group = 2;   // CTA pairs: half the SMEM/L2 operand traffic per MMA
   cudaStream_t st = (cudaStream_t)stream;
   LEMON_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   if (cta_group == 1) {

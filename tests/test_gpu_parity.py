@@ -158,3 +158,134 @@ def test_faiss_compat_api(lb):
     assert (I[:, 4:] == -1).all() and np.isneginf(D[:, 4:]).all()
     with pytest.raises(RuntimeError):
         small.add(x[:, :50])
+
+
+# ------------------------------------------------------------------ tensor-core (tcgen05) path
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("nq,m,d,nseg", [(300, 5000, 128, 1), (1000, 20000, 512, 3), (700, 9000, 768, 1),
+                                         (128, 256, 64, 1), (257, 3001, 200, 2), (5, 70, 512, 1)])
+def test_tc_candidates_match_fp16_matmul(lb, cg, nq, m, d, nseg):
+    """The fused kernel's per-segment top-64 equals top-64 of (fp16 operands, fp32 accumulate)."""
+    import torch
+    x, _, _, _ = clustered_pairs(m, d, n_clusters=max(4, m // 100), seed=m)
+    q = iid_pairs(nq, d, seed=nq)[0] * 0.2 + x[np.arange(nq) % m]
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
+    cv, ci, nseg_out = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+    assert nseg_out == nseg and cv.shape == (nq, nseg * 64)
+    S = (qp.f16.float() @ dbp.f16.float().T).cpu().numpy()
+    cv, ci = cv.cpu().numpy(), ci.cpu().numpy()
+    assert (ci < m).all()
+    seg = cv.reshape(nq, nseg, 64)
+    assert (np.diff(seg, axis=2) <= 0).all()                      # each segment list sorted descending
+    valid = ci >= 0
+    got = np.take_along_axis(S, np.where(valid, ci, 0), 1)
+    np.testing.assert_allclose(cv[valid], got[valid], rtol=0, atol=3e-5)   # reported value == that pair's product
+    kk = min(64, m)
+    order = np.argsort(-cv, axis=1, kind="stable")[:, :kk]
+    mv = np.take_along_axis(cv, order, 1)
+    tv = -np.sort(-S, axis=1)[:, :kk]
+    np.testing.assert_allclose(mv, tv, rtol=0, atol=3e-5)         # merged lists == global top-64 values
+    if m < 64:
+        assert (valid.sum(1) == m).all()
+
+
+def test_tc_error_bound_is_rigorous(lb):
+    """|fp16 tensor-core inner product - float64 inner product| <= eps_row used by the certificate."""
+    from lemon_b200.scoring import ACC_EPS
+    x, y, _, _ = clustered_pairs(6000, 768, n_clusters=40, seed=41)
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(x[:900], True), sc.prepare(x, True)
+    cv, ci, _ = sc.knn_candidates(qp, dbp, nseg=1)
+    cv, ci = cv.cpu().numpy().astype(np.float64), ci.cpu().numpy()
+    q64, db64 = qp.f32.cpu().numpy().astype(np.float64), dbp.f32.cpu().numpy().astype(np.float64)
+    exact = np.einsum("nd,nkd->nk", q64, db64[ci])
+    rs, smax = qp.row_stats.cpu().numpy(), dbp.stats_max.cpu().numpy()
+    eps = rs[:, 2] * smax[1] + rs[:, 0] * smax[2] + ACC_EPS
+    err = np.abs(cv - exact).max(axis=1)
+    assert (err <= eps).all(), (err.max(), eps.min())
+    assert err.max() < 0.25 * eps.min()          # the bound is comfortably loose, not marginal
+
+
+@pytest.mark.parametrize("metric", [0, 1])
+@pytest.mark.parametrize("d,kp", [(512, 31), (768, 51), (96, 6)])
+def test_knn_tc_path_equals_exact_path_bitwise(lb, metric, d, kp):
+    """Tensor-core candidates + fp32 re-rank + certificate/fallback give the SAME lists, bit for bit,
+    as the fp32 brute-force kernel (both report values through the same fp32 summation order)."""
+    x, y, _, _ = clustered_pairs(9000, d, n_clusters=60, seed=d, noise_frac=0.2)
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(y[:1500], True), sc.prepare(y, True)      # text side: contains exact duplicates
+    tv, ti = sc.knn(qp, dbp, kp, metric, mode="tc")
+    info = dict(sc.last_info)
+    ev, ei = sc.knn(qp, dbp, kp, metric, mode="exact")
+    assert (ti == ei).all()
+    assert (tv == ev).all()
+    assert int(info["n_uncertified"].item()) < 0.2 * 1500
+
+
+def test_knn_tc_mass_duplicates_fall_back_exactly(lb):
+    """Classification-style text side (10 distinct vectors): ties span far beyond 64 candidates, every
+    row is uncertified and must be served by the exact GPU fallback with index-ascending ties."""
+    from oracle import lemon_oracle as O
+    x, y, lab, _ = clustered_pairs(3000, 128, n_clusters=30, seed=51, dup_text_classes=10)
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(y[:200], True), sc.prepare(y, True)
+    tv, ti = sc.knn(qp, dbp, 31, 0, mode="tc")
+    assert int(sc.last_info["n_uncertified"].item()) == 200
+    D, I = O.knn_search(qp.f32.cpu().numpy(), dbp.f32.cpu().numpy(), 31, "ip")
+    assert (ti.cpu().numpy() == I).all()
+
+
+@pytest.mark.parametrize("dist_type", ["cosine", "euclidean"])
+def test_score_pairs_tc_mode_vs_oracle(lb, dist_type):
+    x, y, _, mis = clustered_pairs(6000, 512, n_clusters=40, seed=61, noise_frac=0.4)
+    k = 30
+    out = _np(lb.score_pairs(x, y, k=k, dist_type=dist_type, query_in_db=np.arange(6000), hparams=HP, knn_mode="tc"))
+    st = check_against_oracle(out, x, y, x, y, k=k, dist_type=dist_type, query_in_db=np.arange(6000), hparams=HP)
+    assert st["exact_n"] + st["tie_excused_n"] == 6000
+    # sanity: the score separates the injected caption noise (not a parity claim)
+    from sklearn.metrics import roc_auc_score
+    assert roc_auc_score(mis, out["score"]) > 0.7
+
+
+def test_score_pairs_tc_val_split_and_768(lb):
+    x, y, _, _ = clustered_pairs(5000, 768, n_clusters=50, seed=62)
+    out = _np(lb.score_pairs(x[:700], y[:700], x[700:], y[700:], k=15, hparams=HP, knn_mode="tc"))
+    check_against_oracle(out, x[:700], y[:700], x[700:], y[700:], k=15, hparams=HP)
+
+
+def test_full_size_properties_c1_shape(lb):
+    """BASELINE config-1 shape (50k x 512, k=30) through the default path: size-independent properties."""
+    import torch
+    x, y, _, _ = clustered_pairs(50000, 512, n_clusters=1000, seed=71, noise_frac=0.4)
+    n = 50000
+    out = lb.score_pairs(x, y, k=30, query_in_db=np.arange(n), hparams=HP)
+    torch.cuda.synchronize()
+    I_n, I_m = out["I_n"], out["I_m"]
+    ar = torch.arange(n, device=I_n.device)[:, None]
+    assert int((I_n == ar).sum()) == 0                            # self excluded on the image side (no duplicates there)
+    assert bool((I_n >= 0).all()) and bool((I_n < n).all()) and bool((I_m >= 0).all())
+    # D_n = -<x_i,x_j> ascending (best first); dists_m = 1 - <x_i, x_m> in [0,2]
+    assert bool((out["D_n"][:, 1:] >= out["D_n"][:, :-1]).all())
+    assert bool((out["D_m"][:, 1:] >= out["D_m"][:, :-1]).all())
+    assert bool(((out["dists_m"] > -1e-5) & (out["dists_m"] < 2 + 1e-5)).all())
+    # no duplicate neighbours per row
+    srt = torch.sort(I_n, dim=1).values
+    assert int((srt[:, 1:] == srt[:, :-1]).sum()) == 0
+    # idempotence / determinism: a second run is bit-identical
+    out2 = lb.score_pairs(x, y, k=30, query_in_db=np.arange(n), hparams=HP)
+    for c in ("score", "I_n", "I_m", "D_n", "dists_n"):
+        assert bool((out[c] == out2[c]).all()), c
+    # score == d_1 + beta*s_n + gamma*s_m and matches the oracle's formula on the returned records
+    from oracle import lemon_oracle as O
+    sub = slice(0, 4000)
+    rec = {c: out[c][sub].cpu().numpy() for c in ("d_1", "D_n", "D_m", "dists_tr_n", "dists_tr_m", "dists_n", "dists_m")}
+    s, _, _ = O.calc_scores_vectorized(rec, HP)
+    np.testing.assert_allclose(out["score"][sub].cpu().numpy(), s, rtol=1e-6)
+    # neighbour sets of a sample of rows against the float64 oracle
+    rows = np.arange(0, n, 97)[:400]
+    xn = O.normalize_vectors(x)
+    D, I = O.knn_search(xn[rows], xn, 31, "ip")
+    r = O.compare_neighbor_sets(xn[rows], xn, I_n[rows].cpu().numpy(), 30, "ip", D_ref=D[:, 1:], I_ref=I[:, 1:],
+                                top_boundary=D[:, 0])
+    assert r["wrong"] == 0

@@ -17,23 +17,27 @@ t0 = time.time()
 cv, ci, nseg = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
 torch.cuda.synchronize()
 print(f"cg={cg} nq={nq} m={m} d={d} nseg={nseg}: kernel returned in {time.time()-t0:.3f}s")
-S = qp.f16.float() @ dbp.f16.float().T
-cv_h, ci_h = cv.cpu().numpy(), ci.cpu().numpy()
-# merge segments -> top 64 overall
-order = np.argsort(-cv_h, axis=1, kind="stable")[:, :64]
-mv = np.take_along_axis(cv_h, order, 1); mi = np.take_along_axis(ci_h, order, 1)
-tv, ti = torch.topk(S, min(64, m), dim=1)
-tv, ti = tv.cpu().numpy(), ti.cpu().numpy()
-kk = tv.shape[1]
-print("max |val diff| top-%d:" % kk, np.abs(mv[:, :kk] - tv).max())
-same = np.array([len(set(a[:kk]) & set(b)) for a, b in zip(mi, ti)])
-print("set overlap min/mean:", same.min(), same.mean(), " rows fully equal:", (same == kk).mean())
-# gathered check: value reported for idx equals S[row, idx]
-g = np.take_along_axis(S.cpu().numpy(), np.where(mi[:, :kk] < 0, 0, mi[:, :kk]), 1)
-print("max |reported - S[idx]|:", np.abs(g - mv[:, :kk]).max(), " any idx<0:", (mi[:, :kk] < 0).any(), " idx>=m:", (mi >= m).any())
-# per-segment lists sorted descending?
-seg = cv_h.reshape(nq, nseg, 64)
-print("segments sorted desc:", bool((np.diff(seg, axis=2) <= 0).all()))
+if nq * m > 6e8:
+    print("too large to verify, timing only"); S = None
+else:
+    S = qp.f16.float() @ dbp.f16.float().T
+if S is not None:
+  cv_h, ci_h = cv.cpu().numpy(), ci.cpu().numpy()
+  # merge segments -> top 64 overall
+  order = np.argsort(-cv_h, axis=1, kind="stable")[:, :64]
+  mv = np.take_along_axis(cv_h, order, 1); mi = np.take_along_axis(ci_h, order, 1)
+  tv, ti = torch.topk(S, min(64, m), dim=1)
+  tv, ti = tv.cpu().numpy(), ti.cpu().numpy()
+  kk = tv.shape[1]
+  print("max |val diff| top-%d:" % kk, np.abs(mv[:, :kk] - tv).max())
+  same = np.array([len(set(a[:kk]) & set(b)) for a, b in zip(mi, ti)])
+  print("set overlap min/mean:", same.min(), same.mean(), " rows fully equal:", (same == kk).mean())
+  # gathered check: value reported for idx equals S[row, idx]
+  g = np.take_along_axis(S.cpu().numpy(), np.where(mi[:, :kk] < 0, 0, mi[:, :kk]), 1)
+  print("max |reported - S[idx]|:", np.abs(g - mv[:, :kk]).max(), " any idx<0:", (mi[:, :kk] < 0).any(), " idx>=m:", (mi >= m).any())
+  # per-segment lists sorted descending?
+  seg = cv_h.reshape(nq, nseg, 64)
+  print("segments sorted desc:", bool((np.diff(seg, axis=2) <= 0).all()))
 if "--time" in sys.argv:
     for _ in range(3): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
     torch.cuda.synchronize()

@@ -56,6 +56,11 @@ class Prepared:
     d16: int
 
 
+def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
+    return Prepared(p.f32[r0:r1], None if p.f16 is None else p.f16[r0:r1], p.row_stats[r0:r1], p.stats_max,
+                    r1 - r0, p.d, p.d16)
+
+
 def plan_segments(nq: int, m: int, num_sms: int, cta_group: int) -> int:
     """Number of DB segments the tensor-core kernel scans independently.  Work items are
     (row tile, segment); more segments even out the last wave when there are few row
@@ -93,6 +98,7 @@ class LemonScorer:
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.db = None
         self.last_info: dict = {}
+        self.k1_events: list | None = None
 
     # ------------------------------------------------------------------ K0
     def prepare(self, x, normalize: bool = True, need_f16: bool = True) -> Prepared:
@@ -139,13 +145,20 @@ class LemonScorer:
     def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None):
         cg = self.cta_group if cta_group is None else cta_group
         if nseg is None:
-            nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 1)
+            nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2)
         cand_val = torch.empty((q.n, nseg * KPRIME), dtype=torch.float32, device=self.device)
         cand_idx = torch.empty((q.n, nseg * KPRIME), dtype=torch.int32, device=self.device)
+        ev = None
+        if self.k1_events is not None:      # bench.py: per-launch device time of the dominant kernel
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_knn_candidates(self.ctx.handle, _ptr(q.f16), _ptr(db.f16), q.n, db.n, db.d16,
                                                          nseg, cg, _ptr(cand_val), _ptr(cand_idx), _stream()),
                            "lemon_knn_candidates")
+        if ev is not None:
+            ev[1].record()
+            self.k1_events.append((ev[0], ev[1], 2.0 * q.n * db.n * db.d))
         return cand_val, cand_idx, nseg
 
     def rerank(self, q: Prepared, db: Prepared, cand_val, cand_idx, nseg: int, kp: int, metric: int,
@@ -198,17 +211,21 @@ class LemonScorer:
 
     # ------------------------------- run_lemon.py:235-307 + utils.py:47-82
     def score(self, img_q, txt_q, *, k: int, query_in_db=None, hparams: dict | None = None,
-              text_label_ids_q=None, return_records: bool = True, queries_are_db: bool = False) -> dict:
+              text_label_ids_q=None, return_records: bool = True, queries_are_db: bool = False,
+              query_rows: tuple[int, int] | None = None) -> dict:
         """Scores every query pair against the database set by ``set_database``.
 
         query_in_db: None -> val/test rule (search k).  int64[N] (DB row of the query, -1 if
         absent) -> train rule: search k+1, drop rank 0 if present else the last
         (run_lemon.py:257-263).  queries_are_db=True reuses the staged DB operands as queries
-        (N == M, the BASELINE 'N x N' configs) instead of staging them twice."""
+        (N == M, the BASELINE 'N x N' configs) instead of staging them twice; query_rows=(r0, r1)
+        does the same for one rank's block of rows."""
         assert self.db is not None, "call set_database first"
         db = self.db
         metric = db["metric"]
-        if queries_are_db:
+        if query_rows is not None:      # queries = DB rows [r0, r1) (row-sharded multi-GPU): views, no re-staging
+            xq, yq = (_slice_prepared(db[s], *query_rows) for s in ("x", "y"))
+        elif queries_are_db:
             xq, yq = db["x"], db["y"]
         else:
             need16 = self.knn_mode != "exact"

@@ -7,18 +7,20 @@
 //   warp 1   MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
 //                            double-buffered in TMEM (2 x BN columns)
 //   warp 2   TMEM alloc / dealloc
-//   warps 4-7 epilogue    : tcgen05.ld 32x32b (thread == query row), threshold filter in registers,
-//                            survivors appended to a per-row 256-entry buffer (L2-resident global
-//                            scratch), warp-wide bitonic compaction to the best 64 when it fills.
+//   warps 4-11 epilogue   : tcgen05.ld 32x32b (thread == query row), threshold filter in registers,
+//                            8-column groups holding a survivor are staged raw in L2-resident global
+//                            scratch; the warp then filters a row's staged groups cooperatively into the
+//                            row's 256-entry key buffer and prunes it to ~64-160 keys when it fills.
 // Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
 // in the same order and DB tiles are served from L2.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "lemon_common.cuh"
 
 namespace lemon {
 
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 128 + 2 * 128;      // 4 control warps + 2 epilogue groups of 4 warps
 constexpr int kBM = 128;                       // query rows per CTA (TMEM lanes)
 constexpr int kBK = 64;                        // K elements per smem chunk: 128 B rows, SWIZZLE_128B
 constexpr int kAChunkBytes = kBM * kBK * 2;    // 16 KB
@@ -33,7 +35,8 @@ struct TcParams {
   int64_t n_items;      // row_tiles * nseg
   float* cand_val;
   int32_t* cand_idx;
-  uint64_t* scratch;    // [gridDim.x][128][kCap]
+  uint64_t* scratch;    // [gridDim.x] x kScratchPerCta bytes (key buffers + staged groups)
+  int debug;            // LEMON_TC_DEBUG bits: 1 = epilogue does no work, 2 = filter only, 4 = exact-sort compaction
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -54,8 +57,7 @@ __device__ __forceinline__ uint32_t mapa_rank0(uint32_t local_addr) {
   return r;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  const long long t0 = clock64();
+  uint32_t ok = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
@@ -63,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (ok) break;
-    if (clock64() - t0 > 8000000000ll) __trap();   // ~4 s: fail loudly instead of hanging the GPU
+    if (++spins > (1u << 26)) __trap();   // seconds of spinning: fail loudly instead of hanging the GPU
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -140,21 +142,34 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   }
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+// tcgen05.ld 32x32b.x32: thread t of the warp receives columns [c, c+32) of TMEM lane (quadrant*32 + t).
+// Issued asynchronously; tmem_wait_ld ties the registers to the wait so no use can be hoisted above it.
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.wait::ld.sync.aligned;"
+      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+        "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+        "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+        "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+      :
+      : "memory");
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (tile rows are 128 B, 8-row groups 1024 B apart)
@@ -164,34 +179,96 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ---------------------------------------------------------------- streaming top-k (epilogue)
-// Compacts the buffers of all lanes whose count passed `limit`: the warp sorts that lane's 256-slot
-// buffer, keeps the best 64 and raises the lane's threshold to the 64th value.
-__device__ __forceinline__ void compact_rows(uint64_t* warp_buf, int& cnt, float& theta, int limit, int lane) {
+// Warp-wide bitonic sort of 32 keys (one per lane), descending: lane r ends up with rank r.
+__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_xor_u64(key, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      const uint64_t mx = key > o ? key : o, mn = key > o ? o : key;
+      key = keep_max ? mx : mn;
+    }
+  }
+  return key;
+}
+
+constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g owns TMEM accumulator buffer g
+constexpr size_t kKeysPerGroup = size_t(kBM) * kCap;               // uint64 per (CTA, group)
+constexpr size_t kHandoffPerCta = size_t(kBM) * kKeep;             // uint64: group 1 -> group 0 at item end
+constexpr size_t kScratchPerCta = (kEpiGroups * kKeysPerGroup + kHandoffPerCta) * 8;   // 576 KB
+
+// Prunes one row's key buffer `b` (cntL valid keys; all lanes pass the same arguments).  Fast path: a
+// pivot is picked from a sorted systematic sample of the buffer (every 8th slot) such that at least 64
+// keys are >= pivot (counted exactly on the full 64-bit keys, so ties are not an issue); those keys are
+// kept and the row's threshold rises to the pivot's value.  When no sampled pivot qualifies the warp
+// falls back to the exact bitonic sort and keeps exactly the best 64.
+__device__ __forceinline__ void prune_one(uint64_t* b, int& cntL, float& thL, int lane, bool exact_only) {
+  uint64_t key[8];
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
+    key[i] = (lane * 8 + i) < cntL ? t.x : 0ull;
+    key[i + 1] = (lane * 8 + i + 1) < cntL ? t.y : 0ull;
+  }
+  if (!exact_only) {
+    const uint64_t s = warp_sort32_desc(key[0], lane);
+    const uint64_t p0 = shfl_u64(s, 8), p1 = shfl_u64(s, 11), p2 = shfl_u64(s, 15);
+    int c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { c0 += key[i] >= p0; c1 += key[i] >= p1; c2 += key[i] >= p2; }
+    c0 = __reduce_add_sync(kFull, c0); c1 = __reduce_add_sync(kFull, c1); c2 = __reduce_add_sync(kFull, c2);
+    uint64_t pv = 0ull; int keep = 0;
+    if (c0 >= kKeep) { pv = p0; keep = c0; } else if (c1 >= kKeep) { pv = p1; keep = c1; } else if (c2 >= kKeep) { pv = p2; keep = c2; }
+    if (pv != 0ull && keep <= 160) {
+      int mine = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mine += key[i] >= pv;
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+      int pos = incl - mine;
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (key[i] >= pv) { b[pos] = key[i]; ++pos; }
+      __syncwarp();
+      thL = key_val(pv); cntL = keep;
+      return;
+    }
+  }
+  warp_sort256_desc(key, lane);
+  __syncwarp();
+  if (lane < kKeep / 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
+  }
+  const uint64_t k64 = shfl_u64(key[7], kKeep / 8 - 1);
+  if (cntL >= kKeep) { thL = key_val(k64); cntL = kKeep; }
+  __syncwarp();
+}
+
+// Prunes the buffers of all lanes whose key count passed `limit`.
+__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, int& cnt, float& theta, int limit, int lane,
+                                           bool exact_only) {
   unsigned need = __ballot_sync(kFull, cnt > limit);
   while (need) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
-    const int cntL = __shfl_sync(kFull, cnt, L);
-    uint64_t* b = warp_buf + size_t(L) * kCap;
-    uint64_t key[8];
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
-      key[i] = (lane * 8 + i) < cntL ? t.x : 0ull;
-      key[i + 1] = (lane * 8 + i + 1) < cntL ? t.y : 0ull;
-    }
-    warp_sort256_desc(key, lane);
-    if (lane < kKeep / 8) {
-#pragma unroll
-      for (int i = 0; i < 8; i += 2)
-        *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
-    }
-    const uint64_t k64 = shfl_u64(key[7], kKeep / 8 - 1);
-    if (lane == L) {
-      if (cntL >= kKeep) { theta = key_val(k64); cnt = kKeep; }
-    }
-    __syncwarp();
+    int cntL = __shfl_sync(kFull, cnt, L);
+    float thL = __shfl_sync(kFull, theta, L);
+    prune_one(warp_keys + size_t(L) * kCap, cntL, thL, lane, exact_only);
+    if (lane == L) { cnt = cntL; theta = thL; }
   }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ------------------------------------------------------------------------------------ kernel
@@ -199,7 +276,8 @@ template <int CG, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();   // SWIZZLE_128B tiles need 1024 B alignment
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
   const int64_t unit = blockIdx.x / CG;            // CTA (pair) id
@@ -218,6 +296,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const uint32_t tmem_full = a_full + 16;    // [2]
   const uint32_t tmem_empty = a_full + 32;   // [2]
   const uint32_t tmem_slot = a_full + 48;
+  // per-row threshold exchange between the two epilogue groups: [2][128] x (item tag << 32 | float bits)
+  volatile uint64_t* th_sh = reinterpret_cast<volatile uint64_t*>(smem_raw + (a_full + 64 - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
@@ -301,50 +381,86 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp >= 4) {
     // =============================== epilogue: streaming top-64 ===============================
+    // Two groups of 4 warps; group g consumes the tiles that land in TMEM accumulator buffer g, so each
+    // group has two MMA tile-times per tile.  Both groups track the same query rows; each keeps its own
+    // key buffer and they exchange thresholds through shared memory (a threshold certified by either
+    // group is a valid filter for both).  At the end of an item group 1 hands its best 64 per row to
+    // group 0, which merges and writes the candidates.
+    const int grp = (warp - 4) >> 2;
     const int quad = warp & 3;
+    const int row_local = quad * 32 + lane;
     const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
-    uint64_t* warp_buf = p.scratch + (size_t(blockIdx.x) * kBM + size_t(quad) * 32) * kCap;
-    uint64_t* my_buf = warp_buf + size_t(lane) * kCap;
+    uint64_t* cta_scratch = p.scratch + size_t(blockIdx.x) * (kScratchPerCta / 8);
+    uint64_t* warp_keys = cta_scratch + size_t(grp) * kKeysPerGroup + size_t(quad) * 32 * kCap;
+    uint64_t* my_keys = warp_keys + size_t(lane) * kCap;
+    uint64_t* handoff = cta_scratch + kEpiGroups * kKeysPerGroup + size_t(quad) * 32 * kKeep;   // this quadrant's rows
+    const bool exact_only = (p.debug & 4) != 0;
     const uint32_t tempty0 = (CG == 2) ? mapa_rank0(tmem_empty) : tmem_empty;
-    uint32_t tc = 0;
-    for (int64_t item = unit; item < p.n_items; item += n_units) {
+    uint32_t tc = 0, it = 0;
+    for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
       const int64_t rt = item / p.nseg, seg = item % p.nseg;
       const int64_t col0 = seg * p.seg_len;
       const int64_t col1 = min(p.m, col0 + p.seg_len);
       const int64_t ntiles = col1 > col0 ? (col1 - col0 + BN - 1) / BN : 0;
-      const int64_t row = rt * (kBM * CG) + cta_rank * kBM + quad * 32 + lane;
-      float theta = -CUDART_INF_F;
+      const int64_t row = rt * (kBM * CG) + cta_rank * kBM + row_local;
+      const uint64_t tag = uint64_t(uint32_t(item) + 1u) << 32;
+      float theta = (p.debug & 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
+      th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       for (int64_t t = 0; t < ntiles; ++t, ++tc) {
         const uint32_t buf = tc & 1, use = tc >> 1;
+        if (int(buf) != grp) continue;
         mbar_wait(tmem_full + 8 * buf, use & 1);
         tc_fence_after();
+        {   // adopt the other group's threshold for this row if it is tighter (same item only)
+          const uint64_t o = th_sh[(grp ^ 1) * kBM + row_local];
+          if ((o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
+        }
         const int64_t colb = col0 + t * BN;
         const int valid = int(min(int64_t(BN), col1 - colb));
         const uint32_t taddr = tmem_base + tmem_lane + buf * BN;
+        if (!(p.debug & 1)) {
+          const int nchunks = (valid + 31) >> 5;
+          const bool partial = valid < BN;     // only the last tile of a segment
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (c >= valid) break;
-          float v[32];
-          tmem_ld32(taddr + c, v);
-          if (c + 32 > valid) {
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int c = ch * 32;
+            uint32_t r[32];
+            tmem_ld32_async(taddr + c, r);
+            tmem_wait_ld(r);
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (c + j >= valid) v[j] = -CUDART_INF_F;
-          }
-          float mx = v[0];
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (partial) {
 #pragma unroll
-          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-          if (mx > theta) {
-            const uint32_t idx0 = uint32_t(colb + c);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] > theta) { my_buf[cnt] = make_key(v[j], idx0 + j); ++cnt; }
+              for (int j = 0; j < 32; ++j) if (c + j >= valid) v[j] = -CUDART_INF_F;
             }
+            float gm[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float a = fmax3(v[8 * g], v[8 * g + 1], v[8 * g + 2]);
+              const float bq = fmax3(v[8 * g + 3], v[8 * g + 4], v[8 * g + 5]);
+              gm[g] = fmax3(a, bq, fmaxf(v[8 * g + 6], v[8 * g + 7]));
+            }
+            const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+            if (mx > theta) {                  // rare and divergent: append the survivors of the hit groups
+              const uint32_t idx0 = uint32_t(colb + c);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                if (gm[g] > theta) {
+#pragma unroll
+                  for (int j = 8 * g; j < 8 * g + 8; ++j) {
+                    if (v[j] > theta) { my_keys[cnt] = make_key(v[j], idx0 + j); ++cnt; }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, cnt, theta, kCap - 32, lane, exact_only);
           }
-          __syncwarp();
-          if (__any_sync(kFull, cnt > kCap - 32)) compact_rows(warp_buf, cnt, theta, kCap - 32, lane);
         }
-        // hand the accumulator buffer back to the MMA warp
+        // publish this row's threshold and hand the accumulator buffer back to the MMA warp
+        th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -352,18 +468,42 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
         }
       }
-      // item done: sort every row's buffer and emit its best 64 (descending; ties by lower index)
+      // ---- item done: every row's buffer is sorted; group 1 hands its best 64 to group 0, which merges
+      // and emits the best 64 (descending; ties by lower DB index)
       __syncwarp();
+      if (grp == 1 && it > 0) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
       for (int L = 0; L < 32; ++L) {
         const int cntL = __shfl_sync(kFull, cnt, L);
         const int64_t rowL = __shfl_sync(kFull, row, L);
-        uint64_t* b = warp_buf + size_t(L) * kCap;
+        uint64_t* b = warp_keys + size_t(L) * kCap;
         uint64_t key[8];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
           const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
           key[i] = (lane * 8 + i) < cntL ? tt.x : 0ull;
           key[i + 1] = (lane * 8 + i + 1) < cntL ? tt.y : 0ull;
+        }
+        warp_sort256_desc(key, lane);
+        if (grp == 1) {
+          if (lane < kKeep / 8) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2)
+              *reinterpret_cast<ulonglong2*>(handoff + size_t(L) * kKeep + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
+          }
+          continue;
+        }
+        if (L == 0) named_bar_sync(1 + quad, 64);                // group 1's hand-off for this item is complete
+        // merge: lanes 0-7 hold this group's best 64, lanes 8-15 load the other group's
+        if (lane >= kKeep / 8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) key[i] = 0ull;
+          if (lane < 2 * (kKeep / 8)) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(handoff + size_t(L) * kKeep + (lane - kKeep / 8) * 8 + i));
+              key[i] = tt.x; key[i + 1] = tt.y;
+            }
+          }
         }
         warp_sort256_desc(key, lane);
         if (rowL < p.nq && lane < kKeep / 8) {
@@ -383,6 +523,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       __syncwarp();
+      if (grp == 1) named_bar_arrive(1 + quad, 64);             // hand-off written (bar orders the global stores)
+      else named_bar_arrive(5 + quad, 64);                      // hand-off consumed
     }
   }
 
@@ -427,11 +569,12 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const int kchunks = d16 / kBK;
   const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
   const uint32_t stage_bytes = (BN / CG) * kBK * 2;
-  const int64_t avail = int64_t(kMaxSmem) - 1024 /*align*/ - 256 /*barriers*/ - a_bytes;
+  // dynamic shared memory starts 1024-aligned (no static __shared__ in this kernel; checked on the device)
+  const int64_t avail = int64_t(kMaxSmem) - 2304 /*barriers + threshold exchange*/ - a_bytes;
   int nstage = int(avail / stage_bytes);
   if (nstage > 8) nstage = 8;
   if (nstage < 2) return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: d16=%d leaves no room for a DB ring", d16);
-  const size_t smem = 1024 + a_bytes + size_t(nstage) * stage_bytes + 256;
+  const size_t smem = a_bytes + size_t(nstage) * stage_bytes + 2304;
 
   TcParams p;
   p.nq = nq; p.m = m; p.kchunks = kchunks; p.nstage = nstage;
@@ -442,16 +585,18 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const int64_t row_tiles = (nq + kBM * CG - 1) / (kBM * CG);
   p.n_items = row_tiles * nseg;
   p.cand_val = cand_val; p.cand_idx = cand_idx;
+  const char* dbg = getenv("LEMON_TC_DEBUG");
+  p.debug = dbg ? atoi(dbg) : 0;
 
   int64_t units = ctx->num_sms / CG;
   if (units > p.n_items) units = p.n_items;
   const unsigned grid = unsigned(units * CG);
-  const size_t need = size_t(grid) * kBM * kCap * sizeof(uint64_t);
+  const size_t need = size_t(ctx->num_sms) * kScratchPerCta;
   if (ctx->tc_scratch_bytes < need) {
     if (ctx->tc_scratch) LEMON_CUDA_CHECK(ctx, cudaFree(ctx->tc_scratch));
     ctx->tc_scratch = nullptr; ctx->tc_scratch_bytes = 0;
-    LEMON_CUDA_CHECK(ctx, cudaMalloc(&ctx->tc_scratch, size_t(ctx->num_sms) * kBM * kCap * sizeof(uint64_t)));
-    ctx->tc_scratch_bytes = size_t(ctx->num_sms) * kBM * kCap * sizeof(uint64_t);
+    LEMON_CUDA_CHECK(ctx, cudaMalloc(&ctx->tc_scratch, need));
+    ctx->tc_scratch_bytes = need;
   }
   p.scratch = reinterpret_cast<uint64_t*>(ctx->tc_scratch);
 

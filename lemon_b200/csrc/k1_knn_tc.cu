@@ -194,6 +194,8 @@ __device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
   return key;
 }
 
+constexpr int kSoftLimit = 176;                // a row is pruned after a tile once it holds more keys than this
+constexpr int kPrunesPerTile = 3;
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g owns TMEM accumulator buffer g
 constexpr size_t kKeysPerGroup = size_t(kBM) * kCap;               // uint64 per (CTA, group)
 constexpr size_t kHandoffPerCta = size_t(kBM) * kKeep;             // uint64: group 1 -> group 0 at item end
@@ -204,13 +206,17 @@ constexpr size_t kScratchPerCta = (kEpiGroups * kKeysPerGroup + kHandoffPerCta) 
 // keys are >= pivot (counted exactly on the full 64-bit keys, so ties are not an issue); those keys are
 // kept and the row's threshold rises to the pivot's value.  When no sampled pivot qualifies the warp
 // falls back to the exact bitonic sort and keeps exactly the best 64.
-__device__ __forceinline__ void prune_one(uint64_t* b, int& cntL, float& thL, int lane, bool exact_only) {
+__device__ __forceinline__ void load_keys_raw(const uint64_t* b, ulonglong2 (&raw)[4], int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) raw[i] = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + 2 * i));
+}
+__device__ __forceinline__ void prune_one(uint64_t* b, const ulonglong2 (&raw)[4], int& cntL, float& thL, int lane,
+                                          bool exact_only) {
   uint64_t key[8];
 #pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    const ulonglong2 t = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
-    key[i] = (lane * 8 + i) < cntL ? t.x : 0ull;
-    key[i + 1] = (lane * 8 + i + 1) < cntL ? t.y : 0ull;
+  for (int i = 0; i < 4; ++i) {
+    key[2 * i] = (lane * 8 + 2 * i) < cntL ? raw[i].x : 0ull;
+    key[2 * i + 1] = (lane * 8 + 2 * i + 1) < cntL ? raw[i].y : 0ull;
   }
   if (!exact_only) {
     const uint64_t s = warp_sort32_desc(key[0], lane);
@@ -249,19 +255,61 @@ __device__ __forceinline__ void prune_one(uint64_t* b, int& cntL, float& thL, in
   __syncwarp();
 }
 
-// Prunes the buffers of all lanes whose key count passed `limit`.
-__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, int& cnt, float& theta, int limit, int lane,
-                                           bool exact_only) {
+// Prunes the buffers of (at most max_rows of) the lanes whose key count passed `limit`.  The next row's
+// keys are fetched from L2 while the current row is processed.
+__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, int& cnt, float& theta, int limit, int max_rows,
+                                           int lane, bool exact_only) {
   unsigned need = __ballot_sync(kFull, cnt > limit);
-  while (need) {
+  if (!need) return;
+  ulonglong2 raw[4];
+  load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * kCap, raw, lane);
+  while (need && max_rows-- > 0) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
+    ulonglong2 cur[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cur[i] = raw[i];
+    if (need && max_rows > 0) load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * kCap, raw, lane);
     int cntL = __shfl_sync(kFull, cnt, L);
     float thL = __shfl_sync(kFull, theta, L);
-    prune_one(warp_keys + size_t(L) * kCap, cntL, thL, lane, exact_only);
+    prune_one(warp_keys + size_t(L) * kCap, cur, cntL, thL, lane, exact_only);
     if (lane == L) { cnt = cntL; theta = thL; }
   }
   __syncwarp();
+}
+
+// Merge of two descending-sorted 64-key lists into the best 64, descending.  Lanes 0-7 hold list A
+// (lane L: ranks 8L..8L+7); lanes 8-15 hold list B REVERSED (ascending over the 64 slots), so the 128 keys
+// form a bitonic sequence; one half-cleaner step moves the best 64 into lanes 0-7 (still bitonic), six
+// more steps sort them.
+__device__ __forceinline__ void warp_merge_best64_desc(uint64_t (&key)[8], int lane) {
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {                      // j = 64 elements = 8 lanes
+    const uint64_t o = shfl_xor_u64(key[r], 8);
+    const uint64_t mx = key[r] > o ? key[r] : o, mn = key[r] > o ? o : key[r];
+    key[r] = (lane & 8) ? mn : mx;
+  }
+#pragma unroll
+  for (int lm = 4; lm >= 1; lm >>= 1) {              // j = 32, 16, 8 elements
+    const bool lower = (lane & lm) == 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint64_t o = shfl_xor_u64(key[r], lm);
+      const uint64_t mx = key[r] > o ? key[r] : o, mn = key[r] > o ? o : key[r];
+      key[r] = lower ? mx : mn;
+    }
+  }
+#pragma unroll
+  for (int j = 4; j >= 1; j >>= 1) {                 // in-lane
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if ((r & j) == 0) {
+        const uint64_t a = key[r], b = key[r | j];
+        key[r] = a > b ? a : b;
+        key[r | j] = a > b ? b : a;
+      }
+    }
+  }
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -443,11 +491,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               gm[g] = fmax3(a, bq, fmaxf(v[8 * g + 6], v[8 * g + 7]));
             }
             const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-            if (mx > theta) {                  // rare and divergent: append the survivors of the hit groups
+            // warp-uniform gating (votes), so that groups without a survivor in ANY lane are really skipped
+            if (__any_sync(kFull, mx > theta)) {
               const uint32_t idx0 = uint32_t(colb + c);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
-                if (gm[g] > theta) {
+                if (__any_sync(kFull, gm[g] > theta)) {
 #pragma unroll
                   for (int j = 8 * g; j < 8 * g + 8; ++j) {
                     if (v[j] > theta) { my_keys[cnt] = make_key(v[j], idx0 + j); ++cnt; }
@@ -456,7 +505,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               }
             }
             __syncwarp();
-            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, cnt, theta, kCap - 32, lane, exact_only);
+            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow
           }
         }
         // publish this row's threshold and hand the accumulator buffer back to the MMA warp
@@ -467,12 +516,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
           else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
         }
+        // deferred, rate-limited pruning: the accumulator buffer is already released, and at most a few rows
+        // are pruned per tile so that the correlated fill of the 32 rows does not turn into one long stall
+        prune_rows(warp_keys, cnt, theta, kSoftLimit, kPrunesPerTile, lane, exact_only);
+        th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       }
       // ---- item done: every row's buffer is sorted; group 1 hands its best 64 to group 0, which merges
       // and emits the best 64 (descending; ties by lower DB index)
       __syncwarp();
-      if (grp == 1 && it > 0) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
-      for (int L = 0; L < 32; ++L) {
+      if (grp == 1 && it > 0 && !(p.debug & 8)) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
+      for (int L = 0; L < ((p.debug & 8) ? 0 : 32); ++L) {   // debug 8: skip the item-end merge (timing experiments only)
         const int cntL = __shfl_sync(kFull, cnt, L);
         const int64_t rowL = __shfl_sync(kFull, row, L);
         uint64_t* b = warp_keys + size_t(L) * kCap;
@@ -485,15 +538,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         warp_sort256_desc(key, lane);
         if (grp == 1) {
-          if (lane < kKeep / 8) {
+          if (lane < kKeep / 8) {      // reversed: slot s of the hand-off holds rank 63 - s
 #pragma unroll
             for (int i = 0; i < 8; i += 2)
-              *reinterpret_cast<ulonglong2*>(handoff + size_t(L) * kKeep + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
+              *reinterpret_cast<ulonglong2*>(handoff + size_t(L) * kKeep + (kKeep - 8 - lane * 8) + (6 - i)) =
+                  make_ulonglong2(key[i + 1], key[i]);
           }
           continue;
         }
         if (L == 0) named_bar_sync(1 + quad, 64);                // group 1's hand-off for this item is complete
-        // merge: lanes 0-7 hold this group's best 64, lanes 8-15 load the other group's
+        // lanes 0-7 hold this group's best 64 (descending); lanes 8-15 load the other group's, reversed
         if (lane >= kKeep / 8) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) key[i] = 0ull;
@@ -505,7 +559,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             }
           }
         }
-        warp_sort256_desc(key, lane);
+        warp_merge_best64_desc(key, lane);
         if (rowL < p.nq && lane < kKeep / 8) {
           float* ov = p.cand_val + (rowL * p.nseg + seg) * kKeep + lane * 8;
           int32_t* oi = p.cand_idx + (rowL * p.nseg + seg) * kKeep + lane * 8;
@@ -523,8 +577,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       __syncwarp();
-      if (grp == 1) named_bar_arrive(1 + quad, 64);             // hand-off written (bar orders the global stores)
-      else named_bar_arrive(5 + quad, 64);                      // hand-off consumed
+      if (!(p.debug & 8)) {
+        if (grp == 1) named_bar_arrive(1 + quad, 64);             // hand-off written (bar orders the global stores)
+        else named_bar_arrive(5 + quad, 64);                      // hand-off consumed
+      }
     }
   }
 

@@ -61,20 +61,22 @@ def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
                     r1 - r0, p.d, p.d16)
 
 
-def plan_segments(nq: int, m: int, num_sms: int, cta_group: int) -> int:
+def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512) -> int:
     """Number of DB segments the tensor-core kernel scans independently.  Work items are
     (row tile, segment); more segments even out the last wave when there are few row
-    tiles, at the price of nseg*64 candidates per row for the re-rank."""
+    tiles, at the price of nseg*64 candidates per row for the re-rank and of a fixed
+    start-up + merge cost per item (measured on B200: ~0.85 ms at d=512, i.e. the MMA
+    time of ~60k columns)."""
     units = max(1, num_sms // cta_group)
     tiles = max(1, -(-nq // (128 * cta_group)))
+    overhead_cols = 3.0e7 / max(d16, 64)
     best, best_cost = 1, None
     for nseg in (1, 2, 3, 4, 6, 8, 12, 16):
         if nseg > 1 and m // nseg < 4096:
             break
         items = tiles * nseg
         waves = -(-items // units)
-        # time ~ waves * (m / nseg) columns, plus a fixed per-item start-up (~1500 columns' worth)
-        cost = waves * (m / nseg + 1500.0)
+        cost = waves * (m / nseg + overhead_cols)
         if best_cost is None or cost < best_cost * 0.97:
             best, best_cost = nseg, cost
     return best
@@ -145,7 +147,7 @@ class LemonScorer:
     def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None):
         cg = self.cta_group if cta_group is None else cta_group
         if nseg is None:
-            nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2)
+            nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2, db.d16)
         cand_val = torch.empty((q.n, nseg * KPRIME), dtype=torch.float32, device=self.device)
         cand_idx = torch.empty((q.n, nseg * KPRIME), dtype=torch.int32, device=self.device)
         ev = None

@@ -45,11 +45,15 @@ def test_no_cpu_fallback():
 
 def test_plan_segments():
     from lemon_b200 import plan_segments
-    assert plan_segments(3_300_000, 3_300_000, 148, 2) == 1      # many waves: no split
-    assert plan_segments(412_500, 3_300_000, 148, 2) == 1
-    n = plan_segments(14_750, 118_000, 148, 2)                   # C2 on 8 GPUs: 58 pair tiles for 74 pairs
-    assert n > 1
-    assert plan_segments(100, 2000, 148, 2) == 1                 # tiny DB: never split below 4096 columns
+    assert plan_segments(3_300_000, 3_300_000, 148, 2, 768) == 1      # many waves: no split
+    assert plan_segments(412_500, 3_300_000, 148, 2, 768) == 1
+    assert plan_segments(118_000, 118_000, 148, 2, 512) == 1          # per-item start-up outweighs the wave gain
+    assert plan_segments(2_048, 3_300_000, 148, 2, 768) > 1           # 8 pair tiles for 74 pairs, long DB: split it
+    assert plan_segments(100, 2000, 148, 2, 512) == 1                 # tiny DB: never split below 4096 columns
+    for nq in (1, 1000, 50_000):
+        for m in (10, 50_000, 3_300_000):
+            n = plan_segments(nq, m, 148, 2, 512)
+            assert 1 <= n <= 16 and (n == 1 or m // n >= 4096)
 
 
 def test_faiss_shim_installs():

@@ -499,7 +499,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 if (__any_sync(kFull, gm[g] > theta)) {
 #pragma unroll
                   for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                    if (v[j] > theta) { my_keys[cnt] = make_key(v[j], idx0 + j); ++cnt; }
+                    // column vote: the branch is warp-uniform (no reconvergence bookkeeping); only columns
+                    // with a survivor in some lane pay for the (predicated) append
+                    const bool h = v[j] > theta;
+                    if (__any_sync(kFull, h)) {
+                      const uint64_t key = make_key(v[j], idx0 + j);
+                      if (h) { my_keys[cnt] = key; ++cnt; }
+                    }
                   }
                 }
               }

@@ -24,9 +24,28 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const f
     const float* cv = cand_val + row * ncand;
     int cnt = 0;
     __syncwarp();
+    // rounding-error bound of this row (see include/lemon_b200.h) and the candidate cut-off: the kp best
+    // approximate values a_(1..kp) certify kp elements with exact value >= a_(kp) - eps, so a candidate whose
+    // approximate value is below a_(kp) - 2 eps cannot be in the exact top-kp and is not gathered.
+    float eps = 0.f, qsq = 1.f, dbdev = 0.f;
+    if (q_row_stats) {
+      const float4 st = reinterpret_cast<const float4*>(q_row_stats)[row];   // {||q||, ||q16||, ||q-q16||, ||q||^2}
+      eps = st.z * db_stats_max[1] + st.x * db_stats_max[2] + acc_eps;
+      qsq = st.w;
+      dbdev = db_stats_max[3];
+    }
+    float akp = -CUDART_INF_F;
+    for (int s = lane; s < nseg; s += 32) {
+      const int pos = s * kKeep + kp - 1;
+      if (ci[pos] >= 0) akp = fmaxf(akp, cv[pos]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) akp = fmaxf(akp, __shfl_xor_sync(kFull, akp, o));
+    const float cut = akp - 2.f * eps - (METRIC == LEMON_METRIC_L2 ? dbdev : 0.f);
     for (int c0 = 0; c0 < ncand; c0 += 32) {
       // lanes fetch 32 candidate ids at once, then the warp evaluates them one by one
-      const int my = (c0 + lane) < ncand ? ci[c0 + lane] : -1;
+      int my = (c0 + lane) < ncand ? ci[c0 + lane] : -1;
+      if (my >= 0 && cv[c0 + lane] < cut) my = -1;
       const int nc = min(32, ncand - c0);
       for (int t = 0; t < nc; ++t) {
         const int idx = __shfl_sync(kFull, my, t);
@@ -82,13 +101,7 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const f
     for (int i = 0; i < 8; ++i) if (i == ((kp - 1) & 7)) kth_sel = key[i];
     const uint64_t kth_key = shfl_u64(kth_sel, (kp - 1) >> 3);
     if (lane == 0 && B > -CUDART_INF_F) {
-      float eps = 0.f, qsq = 1.f, dbmin = 1.f;
-      if (q_row_stats) {
-        const float4 st = reinterpret_cast<const float4*>(q_row_stats)[row];   // {||q||, ||q16||, ||q-q16||, ||q||^2}
-        eps = st.z * db_stats_max[1] + st.x * db_stats_max[2] + acc_eps;
-        qsq = st.w;
-        dbmin = 1.f - db_stats_max[3];
-      }
+      const float dbmin = 1.f - dbdev;
       float T = B + eps;
       if (METRIC == LEMON_METRIC_L2) T = 2.f * T - qsq - dbmin;
       const bool certified = kth_key != 0ull && key_val(kth_key) > T;

@@ -116,6 +116,8 @@ int lemon_knn_exact(lemon_ctx* ctx, const float* q, const float* db, const int32
  *   topn_* / topm_* [nq, kp]: image-kNN / text-kNN top lists, kp = k + 1 when query_in_db != NULL else k
  *   query_in_db [nq] int64 or NULL: train-split rule (>=0: drop rank 0, -1: drop the last)
  *   label_q [nq], label_db [m] int32 or NULL: discrete text metric (--use_discrete_for_text)
+ *   class_emb [n_class, d], noisy_label [nq] int32 or NULL: --normalize_d1 (run_lemon.py:244-248):
+ *     d_1 = softmax_c(1 - <x_i, T_c>)[noisy_label_i]  (cosine)  /  softmax_c(||x_i - T_c||^2)[noisy_label_i]  (euclidean)
  *   hp[6] = {beta, gamma, tau_1_n, tau_2_n, tau_1_m, tau_2_m}: HOST pointer read at call time, or NULL
  *   (then sn/sm/score are not written)
  *   outputs (any may be NULL): d1 [nq]; Dn,dists_n,dists_tr_n,Dm,dists_m,dists_tr_m [nq,k] fp32;
@@ -124,7 +126,8 @@ int lemon_knn_exact(lemon_ctx* ctx, const float* q, const float* db, const int32
 int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* xdb, const float* ydb,
                 const float* dists_tr, const float* topn_val, const int32_t* topn_idx,
                 const float* topm_val, const int32_t* topm_idx, const int64_t* query_in_db,
-                const int32_t* label_q, const int32_t* label_db, int64_t nq, int64_t m, int d, int k,
+                const int32_t* label_q, const int32_t* label_db, const float* class_emb,
+                const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                 int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
                 float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, int64_t* In,
                 int64_t* Im, double* sn, double* sm, double* score, void* stream);

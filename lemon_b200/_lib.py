@@ -35,8 +35,8 @@ SIGNATURES = {
     "lemon_knn_exact": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_int, C.c_int, C.c_int, c_f32p, c_i32p, C.c_void_p]),
     "lemon_score": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p,
-                              c_i64p, c_i32p, c_i32p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
-                              C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64p,
+                              c_i64p, c_i32p, c_i32p, c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
+                              C.c_int, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64p,
                               c_i64p, c_f64p, c_f64p, c_f64p, C.c_void_p]),
     "lemon_combine_scores": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f64p, C.c_int64,
                                        C.c_int, C.POINTER(C.c_double), c_f64p, c_f64p, c_f64p, C.c_void_p]),

@@ -196,6 +196,8 @@ __device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
 
 constexpr int kSoftLimit = 176;                // a row is pruned after a tile once it holds more keys than this
 constexpr int kPrunesPerTile = 3;
+constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
+constexpr int kBootMinTiles = 64;              // items shorter than this run without the bootstrap
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g owns TMEM accumulator buffer g
 constexpr size_t kKeysPerGroup = size_t(kBM) * kCap;               // uint64 per (CTA, group)
 constexpr size_t kHandoffPerCta = size_t(kBM) * kKeep;             // uint64: group 1 -> group 0 at item end
@@ -312,6 +314,44 @@ __device__ __forceinline__ void warp_merge_best64_desc(uint64_t (&key)[8], int l
   }
 }
 
+// Warp-wide bitonic sort of 32 floats (one per lane), descending: lane r ends up with rank r.
+__device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const float o = __shfl_xor_sync(kFull, x, j);
+      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+      x = keep_max ? fmaxf(x, o) : fminf(x, o);
+    }
+  }
+  return x;
+}
+
+// Threshold bootstrap.  During an item's first tiles a group only records the maxima of its 8-column groups
+// (128 floats per row, kept in the row's still unused key buffer).  Every group maximum is a distinct DB
+// column, so a value with at least 64 recorded maxima >= it is a valid threshold (at least 64 columns beat it),
+// and it is nearly as tight as the true 64th best of those tiles.  The pivot comes from a sorted sample with
+// an exact count, as in prune_one.  The bootstrap tiles are re-scanned at the end of the item.
+__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, float& theta, int lane) {
+  for (int L = 0; L < 32; ++L) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(warp_keys + size_t(L) * kCap) + lane);
+    const float s = warp_sort32_desc_f(v.x, lane);
+    const float p0 = __shfl_sync(kFull, s, 13), p1 = __shfl_sync(kFull, s, 16), p2 = __shfl_sync(kFull, s, 20);
+    const float p3 = __shfl_sync(kFull, s, 31);
+    int c0 = (v.x >= p0) + (v.y >= p0) + (v.z >= p0) + (v.w >= p0);
+    int c1 = (v.x >= p1) + (v.y >= p1) + (v.z >= p1) + (v.w >= p1);
+    int c2 = (v.x >= p2) + (v.y >= p2) + (v.z >= p2) + (v.w >= p2);
+    c0 = __reduce_add_sync(kFull, c0); c1 = __reduce_add_sync(kFull, c1); c2 = __reduce_add_sync(kFull, c2);
+    float mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+    (void)p3;
+    const float th = c0 >= kKeep ? p0 : (c1 >= kKeep ? p1 : (c2 >= kKeep ? p2 : mn));   // mn: all 128 maxima >= it
+    if (lane == L) theta = fmaxf(theta, th);
+  }
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -333,6 +373,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   constexpr int kBRows = BN / CG;                  // DB rows this CTA stages per tile
   constexpr uint32_t kStageBytes = kBRows * kBK * 2;
   constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr int kBoot = kBootTiles * 256 / BN;     // bootstrap tiles per item: 128 group maxima per epilogue group
 
   const uint32_t a_smem = smem_base;
   const uint32_t b_smem = a_smem + uint32_t(p.kchunks) * kAChunkBytes;
@@ -382,7 +423,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (cta_rank == 0) mbar_arrive_expect_tx(a_full, uint32_t(p.kchunks) * kAChunkBytes * CG);
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d<CG>(a_smem + kc * kAChunkBytes, &map_q, afull_l, kc * kBK, row0);
-        for (int64_t t = 0; t < ntiles; ++t) {
+        const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);   // bootstrap tiles are scanned twice
+        for (int64_t i = 0; i < nsteps; ++i) {
+          const int64_t t = i < ntiles ? i : i - ntiles;
           const int dbrow = int(col0 + t * BN + cta_rank * kBRows);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1);
@@ -406,7 +449,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (ntiles == 0) { --it; continue; }
         mbar_wait(a_full, it & 1);
         tc_fence_after();
-        for (int64_t t = 0; t < ntiles; ++t, ++tc) {
+        const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);
+        for (int64_t i = 0; i < nsteps; ++i, ++tc) {
           const uint32_t buf = tc & 1, use = tc >> 1;
           mbar_wait(tmem_empty + 8 * buf, (use & 1) ^ 1);
           tc_fence_after();
@@ -435,6 +479,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // group is a valid filter for both).  At the end of an item group 1 hands its best 64 per row to
     // group 0, which merges and writes the candidates.
     const int grp = (warp - 4) >> 2;
+    const bool one_group = (p.debug & 32) != 0;     // experiment: a single epilogue group consumes every tile
+    if (!(one_group && grp == 1)) {
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
@@ -455,14 +501,51 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       float theta = (p.debug & 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
       th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
-      for (int64_t t = 0; t < ntiles; ++t, ++tc) {
+      const int nboot = ntiles >= kBootMinTiles ? kBoot : 0;
+      const int64_t nsteps = ntiles + nboot;
+      int bcount = 0;
+      for (int64_t i = 0; i < nsteps; ++i, ++tc) {
+        const int64_t t = i < ntiles ? i : i - ntiles;
         const uint32_t buf = tc & 1, use = tc >> 1;
-        if (int(buf) != grp) continue;
+        if (!one_group && int(buf) != grp) continue;
         mbar_wait(tmem_full + 8 * buf, use & 1);
         tc_fence_after();
+        if (i < nboot && bcount >= 0) {
+          // ---- bootstrap tile: record the 8-column group maxima only (no appends, no prunes)
+          const uint32_t taddr_b = tmem_base + tmem_lane + buf * BN;
+          float4* bf = reinterpret_cast<float4*>(my_keys) + bcount * (BN / 32);
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t r[32];
+            tmem_ld32_async(taddr_b + ch * 32, r);
+            tmem_wait_ld(r);
+            float gm[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const float a = fmax3(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]), __uint_as_float(r[8 * g + 2]));
+              const float bq = fmax3(__uint_as_float(r[8 * g + 3]), __uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+              gm[g] = fmax3(a, bq, fmaxf(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7])));
+            }
+            bf[ch] = make_float4(gm[0], gm[1], gm[2], gm[3]);
+          }
+          ++bcount;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
+          }
+          if (bcount * (BN / 8) >= 128) {   // (single-group mode records 8 tiles but uses the first 4)            // 128 maxima recorded (4 tiles of 256 columns): set the thresholds
+            boot_select(warp_keys, theta, lane);
+            __syncwarp();
+            th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
+            bcount = -1000000;
+          }
+          continue;
+        }
         {   // adopt the other group's threshold for this row if it is tighter (same item only)
           const uint64_t o = th_sh[(grp ^ 1) * kBM + row_local];
-          if ((o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
+          if (!one_group && (o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
         }
         const int64_t colb = col0 + t * BN;
         const int valid = int(min(int64_t(BN), col1 - colb));
@@ -499,13 +582,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
                 if (__any_sync(kFull, gm[g] > theta)) {
 #pragma unroll
                   for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                    // column vote: the branch is warp-uniform (no reconvergence bookkeeping); only columns
-                    // with a survivor in some lane pay for the (predicated) append
-                    const bool h = v[j] > theta;
-                    if (__any_sync(kFull, h)) {
-                      const uint64_t key = make_key(v[j], idx0 + j);
-                      if (h) { my_keys[cnt] = key; ++cnt; }
-                    }
+                    if (v[j] > theta) { my_keys[cnt] = make_key(v[j], idx0 + j); ++cnt; }
                   }
                 }
               }
@@ -530,7 +607,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       // ---- item done: every row's buffer is sorted; group 1 hands its best 64 to group 0, which merges
       // and emits the best 64 (descending; ties by lower DB index)
       __syncwarp();
-      if (grp == 1 && it > 0 && !(p.debug & 8)) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
+      if (grp == 1 && it > 0 && !(p.debug & 8) && !one_group) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
       for (int L = 0; L < ((p.debug & 8) ? 0 : 32); ++L) {   // debug 8: skip the item-end merge (timing experiments only)
         const int cntL = __shfl_sync(kFull, cnt, L);
         const int64_t rowL = __shfl_sync(kFull, row, L);
@@ -552,12 +629,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           }
           continue;
         }
-        if (L == 0) named_bar_sync(1 + quad, 64);                // group 1's hand-off for this item is complete
+        if (L == 0 && !one_group) named_bar_sync(1 + quad, 64);  // group 1's hand-off for this item is complete
         // lanes 0-7 hold this group's best 64 (descending); lanes 8-15 load the other group's, reversed
         if (lane >= kKeep / 8) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) key[i] = 0ull;
-          if (lane < 2 * (kKeep / 8)) {
+          if (lane < 2 * (kKeep / 8) && !one_group) {
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
               const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(handoff + size_t(L) * kKeep + (lane - kKeep / 8) * 8 + i));
@@ -583,11 +660,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       __syncwarp();
-      if (!(p.debug & 8)) {
+      if (!(p.debug & 8) && !one_group) {
         if (grp == 1) named_bar_arrive(1 + quad, 64);             // hand-off written (bar orders the global stores)
         else named_bar_arrive(5 + quad, 64);                      // hand-off consumed
       }
     }
+    }   // !(one_group && grp == 1)
   }
 
   // =============================== teardown ===============================

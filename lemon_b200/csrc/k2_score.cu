@@ -16,8 +16,9 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
              const float* __restrict__ ydb, const float* __restrict__ dists_tr, const float* __restrict__ topn_val,
              const int32_t* __restrict__ topn_idx, const float* __restrict__ topm_val,
              const int32_t* __restrict__ topm_idx, const int64_t* __restrict__ query_in_db,
-             const int32_t* __restrict__ label_q, const int32_t* __restrict__ label_db, int64_t nq, int64_t m, int d,
-             int k, int kp, ScoreHp hp, float* __restrict__ d1, float* __restrict__ Dn, float* __restrict__ dists_n,
+             const int32_t* __restrict__ label_q, const int32_t* __restrict__ label_db,
+             const float* __restrict__ class_emb, const int32_t* __restrict__ noisy_label, int n_class, int64_t nq,
+             int64_t m, int d, int k, int kp, ScoreHp hp, float* __restrict__ d1, float* __restrict__ Dn, float* __restrict__ dists_n,
              float* __restrict__ dists_tr_n, float* __restrict__ Dm, float* __restrict__ dists_m,
              float* __restrict__ dists_tr_m, int64_t* __restrict__ In, int64_t* __restrict__ Im,
              double* __restrict__ sn, double* __restrict__ sm, double* __restrict__ score) {
@@ -29,8 +30,29 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
     const float* xr = xq + row * d;
     const float* yr = yq + row * d;
     // d_1 (run_lemon.py:250-253)
-    float pv = warp_pair_value<METRIC>(xr, yr, d, lane);
-    const float d1v = (METRIC == LEMON_METRIC_IP) ? 1.0f - pv : pv;
+    float d1v;
+    if (class_emb == nullptr) {
+      const float pv = warp_pair_value<METRIC>(xr, yr, d, lane);
+      d1v = (METRIC == LEMON_METRIC_IP) ? 1.0f - pv : pv;
+    } else {
+      // --normalize_d1 (run_lemon.py:244-248): softmax over the class prompts of the image-to-prompt
+      // distances, read at the sample's noisy label (max-subtracted like scipy.special.softmax)
+      const int lab = noisy_label[row];
+      float mxv = -CUDART_INF_F, dl = 0.f;
+      for (int c = 0; c < n_class; ++c) {
+        const float pv = warp_pair_value<METRIC>(xr, class_emb + int64_t(c) * d, d, lane);
+        const float dc = (METRIC == LEMON_METRIC_IP) ? 1.0f - pv : pv;
+        mxv = fmaxf(mxv, dc);
+        if (c == lab) dl = dc;
+      }
+      float den = 0.f;
+      for (int c = 0; c < n_class; ++c) {
+        const float pv = warp_pair_value<METRIC>(xr, class_emb + int64_t(c) * d, d, lane);
+        const float dc = (METRIC == LEMON_METRIC_IP) ? 1.0f - pv : pv;
+        den += expf(dc - mxv);
+      }
+      d1v = (lab >= 0 && lab < n_class) ? expf(dl - mxv) / den : __int_as_float(0x7fc00000);
+    }
     // self-exclusion (run_lemon.py:257-263, 277-283): kp == k+1 -> drop rank 0 if in DB else the last
     const int off = (query_in_db != nullptr && query_in_db[row] >= 0) ? 1 : 0;
     double acc_n = 0.0, acc_m = 0.0;
@@ -138,7 +160,8 @@ static ScoreHp make_hp(const double* hp) {
 extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* xdb, const float* ydb,
                            const float* dists_tr, const float* topn_val, const int32_t* topn_idx,
                            const float* topm_val, const int32_t* topm_idx, const int64_t* query_in_db,
-                           const int32_t* label_q, const int32_t* label_db, int64_t nq, int64_t m, int d, int k,
+                           const int32_t* label_q, const int32_t* label_db, const float* class_emb,
+                           const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                            int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
                            float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, int64_t* In,
                            int64_t* Im, double* sn, double* sm, double* score, void* stream) {
@@ -146,7 +169,8 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
   if (!ctx) return LEMON_ERR_INVALID;
   if (!xq || !yq || !xdb || !ydb || !dists_tr || !topn_val || !topn_idx || !topm_val || !topm_idx || nq < 0 || d <= 0 ||
       k < 1 || k > 64 || (kp != k && kp != k + 1) || (query_in_db && kp != k + 1) || (!query_in_db && kp != k) ||
-      ((label_q == nullptr) != (label_db == nullptr)))
+      ((label_q == nullptr) != (label_db == nullptr)) || ((class_emb == nullptr) != (noisy_label == nullptr)) ||
+      (class_emb && n_class < 1))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "score: bad args (kp must be k+1 with query_in_db, k without)");
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kScWarps - 1) / kScWarps;
@@ -155,12 +179,12 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
   const ScoreHp h = make_hp(hp);
   if (metric == LEMON_METRIC_IP)
     score_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
-        xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, nq, m, d, k,
-        kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
+        xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
   else
     score_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
-        xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, nq, m, d, k,
-        kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
+        xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());
   return LEMON_OK;

@@ -214,7 +214,7 @@ class LemonScorer:
     # ------------------------------- run_lemon.py:235-307 + utils.py:47-82
     def score(self, img_q, txt_q, *, k: int, query_in_db=None, hparams: dict | None = None,
               text_label_ids_q=None, return_records: bool = True, queries_are_db: bool = False,
-              query_rows: tuple[int, int] | None = None) -> dict:
+              query_rows: tuple[int, int] | None = None, class_text_emb=None, noisy_label=None) -> dict:
         """Scores every query pair against the database set by ``set_database``.
 
         query_in_db: None -> val/test rule (search k).  int64[N] (DB row of the query, -1 if
@@ -241,6 +241,12 @@ class LemonScorer:
         lab_db = db["labels"] if lab_q is not None else None
         if lab_q is not None and lab_db is None:
             raise ValueError("text_label_ids_q given but the database has no text_label_ids_db")
+        cls_emb = n_class = lab_noisy = None
+        if class_text_emb is not None:     # --normalize_d1: class prompts are normalised like every other embedding
+            cls_p = self.prepare(class_text_emb, db["normalize"], need_f16=False)
+            cls_emb, n_class = cls_p.f32, cls_p.n
+            lab_noisy = _to_dev(noisy_label, self.device, torch.int32)
+            assert lab_noisy is not None and lab_noisy.numel() == nq and cls_p.d == db["x"].d
         topn = self.knn(xq, db["x"], kp, metric)
         info_n = self.last_info
         topm = self.knn(yq, db["y"], kp, metric)
@@ -263,7 +269,7 @@ class LemonScorer:
             self.ctx.check(self.lib.lemon_score(
                 self.ctx.handle, _ptr(xq.f32), _ptr(yq.f32), _ptr(db["x"].f32), _ptr(db["y"].f32), _ptr(db["dists_tr"]),
                 _ptr(topn[0]), _ptr(topn[1]), _ptr(topm[0]), _ptr(topm[1]), _ptr(qid), _ptr(lab_q), _ptr(lab_db),
-                nq, db["x"].n, db["x"].d, k, kp, metric, hp_arr, g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"),
+                _ptr(cls_emb), _ptr(lab_noisy), int(n_class or 0), nq, db["x"].n, db["x"].d, k, kp, metric, hp_arr, g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"),
                 g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"), g("s_n"), g("s_m"), g("score"),
                 _stream()), "lemon_score")
         self.last_info = {"img": info_n, "txt": info_m}
@@ -299,10 +305,11 @@ def get_scorer(device=None, knn_mode: str = "auto") -> LemonScorer:
 def score_pairs(img_q, txt_q, img_db=None, txt_db=None, *, k: int, dist_type: str = "cosine",
                 query_in_db=None, hparams: dict | None = None, text_label_ids_q=None, text_label_ids_db=None,
                 normalize: bool = True, return_records: bool = True, to_host: bool = False, device=None,
-                knn_mode: str = "auto") -> dict:
+                knn_mode: str = "auto", class_text_emb=None, noisy_label=None) -> dict:
     """Fused replacement of run_lemon.py:163-314 + :406-407 in one call (SURVEY.md §8b seam 3).
 
-    img_db/txt_db None means DB == queries (N == M).  Returns the df columns of
+    img_db/txt_db None means DB == queries (N == M).  class_text_emb [C,d] + noisy_label [N] select the
+    --normalize_d1 variant of d_1 (run_lemon.py:244-248).  Returns the df columns of
     run_lemon.py:291-307 as tensors: d_1 [N]; D_n, dists_n, dists_tr_n, D_m, dists_m, dists_tr_m
     [N,k] fp32; I_n, I_m [N,k] int64; and, with hparams, s_n, s_m, score [N] float64."""
     sc = get_scorer(device, knn_mode)
@@ -310,7 +317,8 @@ def score_pairs(img_q, txt_q, img_db=None, txt_db=None, *, k: int, dist_type: st
     sc.set_database(img_q if same else img_db, txt_q if same else txt_db, dist_type, normalize, text_label_ids_db
                     if not same or text_label_ids_db is not None else text_label_ids_q)
     out = sc.score(img_q, txt_q, k=k, query_in_db=query_in_db, hparams=hparams, text_label_ids_q=text_label_ids_q,
-                   return_records=return_records, queries_are_db=same)
+                   return_records=return_records, queries_are_db=same, class_text_emb=class_text_emb,
+                   noisy_label=noisy_label)
     if to_host:
         out = {name: t.cpu().numpy() for name, t in out.items()}
     return out

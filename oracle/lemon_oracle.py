@@ -154,7 +154,7 @@ def apply_self_exclusion(D: np.ndarray, I: np.ndarray, in_db: np.ndarray) -> tup
 
 # ----------------------------------------------------------------------- a6-a10
 def build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type: str,
-                  text_label_ids_q=None, text_label_ids_db=None) -> dict:
+                  text_label_ids_q=None, text_label_ids_db=None, class_text_emb=None, noisy_label=None) -> dict:
     """Vectorised restatement of the per-sample loop body run_lemon.py:250-307 for
     given (already self-excluded) neighbour lists.  float64 arithmetic.
 
@@ -170,6 +170,11 @@ def build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type: s
     cos = dist_type == "cosine"
     N, k = I_n.shape
     d_1 = (1.0 - (xq * yq).sum(1)) if cos else ((xq - yq) ** 2).sum(1)       # :250-253
+    if class_text_emb is not None:                                            # --normalize_d1, :244-248
+        T = np.asarray(class_text_emb, np.float64)
+        dc = (1.0 - xq @ T.T) if cos else ((xq[:, None, :] - T[None]) ** 2).sum(-1)
+        e = np.exp(dc - dc.max(axis=1, keepdims=True))                        # scipy.special.softmax
+        d_1 = (e / e.sum(axis=1, keepdims=True))[np.arange(N), np.asarray(noisy_label)]
     dists_n = np.empty((N, k))
     dists_m = np.empty((N, k))
     bs = 1024
@@ -228,7 +233,8 @@ def calc_scores_loop(rec: dict, hp: dict) -> tuple[np.ndarray, np.ndarray, np.nd
 # ----------------------------------------------------------------- whole path
 def lemon_oracle(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str = "cosine",
                  query_in_db=None, hparams: dict | None = None, normalize: bool = True,
-                 text_label_ids_q=None, text_label_ids_db=None, given_I=None) -> dict:
+                 text_label_ids_q=None, text_label_ids_db=None, given_I=None, class_text_emb=None,
+                 noisy_label=None) -> dict:
     """Truth oracle for the whole path (run_lemon.py:163-176, 235-307 + utils.py:47-82).
 
     query_in_db: None for val/test-style queries (search k, keep all), or int64[N]
@@ -254,8 +260,10 @@ def lemon_oracle(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str = "cosi
         I_n, I_m = (np.asarray(a, np.int64) for a in given_I)
         D_n = pair_values(img_q, img_db, I_n, metric)
         D_m = pair_values(txt_q, txt_db, I_m, metric)
+    if class_text_emb is not None and normalize:
+        class_text_emb = normalize_vectors(class_text_emb)
     rec = build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type,
-                        text_label_ids_q, text_label_ids_db)
+                        text_label_ids_q, text_label_ids_db, class_text_emb, noisy_label)
     rec["I_n"], rec["I_m"] = I_n, I_m
     if hparams is not None:
         rec["score"], rec["s_n"], rec["s_m"] = calc_scores_vectorized(rec, hparams)

@@ -289,3 +289,41 @@ def test_full_size_properties_c1_shape(lb):
     r = O.compare_neighbor_sets(xn[rows], xn, I_n[rows].cpu().numpy(), 30, "ip", D_ref=D[:, 1:], I_ref=I[:, 1:],
                                 top_boundary=D[:, 0])
     assert r["wrong"] == 0
+
+
+@pytest.mark.parametrize("dist_type", ["cosine", "euclidean"])
+def test_normalize_d1_variant(lb, dist_type):
+    """--normalize_d1 (run_lemon.py:244-248): d_1 = softmax over class prompts read at the noisy label."""
+    from oracle import lemon_oracle as O
+    x, y, lab, _ = clustered_pairs(700, 64, n_clusters=20, seed=81, dup_text_classes=10)
+    protos = np.stack([y[np.nonzero(lab == c)[0][0]] for c in range(10)]) * 1.3     # un-normalised class prompts
+    noisy = (lab + (np.arange(700) % 3 == 0)) % 10
+    out = _np(lb.score_pairs(x, y, k=6, dist_type=dist_type, query_in_db=np.arange(700), hparams=HP, knn_mode="exact",
+                             class_text_emb=protos, noisy_label=noisy, text_label_ids_q=lab, text_label_ids_db=lab))
+    ref = O.lemon_oracle(x, y, x, y, k=6, dist_type=dist_type, query_in_db=np.arange(700), hparams=HP,
+                         class_text_emb=protos, noisy_label=noisy, text_label_ids_q=lab, text_label_ids_db=lab)
+    np.testing.assert_allclose(out["d_1"], ref["d_1"], rtol=1e-5, atol=1e-7)
+    assert ((out["d_1"] > 0) & (out["d_1"] < 1)).all()
+    same = (out["I_n"] == ref["I_n"]).all(1) & (out["I_m"] == ref["I_m"]).all(1)
+    np.testing.assert_allclose(out["score"][same], ref["score"][same], rtol=1e-5)
+
+
+@pytest.mark.parametrize("seed,n,d,k", [(1, 1500, 512, 1), (2, 1999, 768, 2), (3, 777, 512, 5), (4, 2048, 768, 10),
+                                        (5, 1300, 512, 15), (6, 1800, 768, 20), (7, 900, 512, 30), (8, 2000, 768, 50)])
+def test_property_grid_default_path_vs_oracle(lb, seed, n, d, k):
+    """SURVEY.md §4 property grid: random N <= 2k, d in {512,768}, k in the reference's k grid
+    (experiments.py:86); default (tensor-core) path; sets == float64 oracle modulo eps-ties, scores <= 1e-5."""
+    x, y, _, _ = clustered_pairs(n, d, n_clusters=max(4, n // 60), seed=100 + seed, noise_frac=0.25)
+    out = _np(lb.score_pairs(x, y, k=k, query_in_db=np.arange(n), hparams=HP))
+    st = check_against_oracle(out, x, y, x, y, k=k, query_in_db=np.arange(n), hparams=HP)
+    assert st["exact_n"] + st["tie_excused_n"] == n and st["exact_m"] + st["tie_excused_m"] == n
+
+
+def test_results_adapter_feeds_metrics_compat(lb):
+    """fused path -> legacy DataFrame (run_lemon.py:291-314 schema) -> drop-in scoring function: same scores."""
+    from lemon_b200 import results, metrics_compat
+    x, y, _, mis = clustered_pairs(1200, 128, n_clusters=20, seed=91, noise_frac=0.3)
+    out = lb.score_pairs(x, y, k=9, query_in_db=np.arange(1200), hparams=HP)
+    df = results.records_to_dataframe(out, "train", is_mislabel=mis)
+    s = metrics_compat.calc_scores_given_hparams_vectorized(df, HP)
+    np.testing.assert_allclose(s, out["score"].cpu().numpy(), rtol=1e-6)

@@ -26,7 +26,8 @@ sys.path.insert(0, ROOT)
 
 HP = {"beta": 5.0, "gamma": 5.0, "tau_1_n": 0.1, "tau_2_n": 5.0, "tau_1_m": 0.1, "tau_2_m": 5.0}  # train_clip_from_scratch.py:102-109
 WORKLOADS = {  # BASELINE.json configs
-    "c1": dict(n=50_000, d=512, k=30, noise=0.0, name="C1 CIFAR-10-shaped: 50k pairs, 512-d, k=30"),
+    "c1": dict(n=50_000, d=512, k=30, noise=0.0, text_classes=10,
+               name="C1 CIFAR-10-shaped: 50k pairs, 512-d, k=30, text side = 10 distinct prompt vectors, discrete text metric"),
     "c2": dict(n=118_000, d=512, k=30, noise=0.4, name="C2 MSCOCO-shaped: 118k pairs, 512-d, cat noise 0.4, k=30"),
     "c3": dict(n=370_000, d=512, k=30, noise=0.0, name="C3 MIMIC-CXR-shaped: 370k pairs, 512-d, k=30"),
     "c4": dict(n=3_300_000, d=768, k=30, noise=0.0, name="C4 CC3M-shaped: 3.3M pairs, 768-d, k=30"),
@@ -35,7 +36,7 @@ WORKLOADS = {  # BASELINE.json configs
 METRIC = "LEMoN pairs scored/s"
 
 
-def synth_pairs(n, d, noise, seed, device):
+def synth_pairs(n, d, noise, seed, device, text_classes=0):
     """clustered unit-norm CLIP-like embeddings (1000 centroids) + 'cat' caption noise
     (a caption replaced by another caption of the same cluster: exact duplicate text rows)."""
     import torch
@@ -47,6 +48,10 @@ def synth_pairs(n, d, noise, seed, device):
     x = cen[z] + 0.6 * torch.randn(n, d, generator=g, device=device)
     y = 0.5 * x + 0.5 * cen2[z] + 0.6 * torch.randn(n, d, generator=g, device=device)
     mis = torch.zeros(n, dtype=torch.bool, device=device)
+    if text_classes:     # classification datasets: every caption is one of `text_classes` prompt embeddings (exact duplicates)
+        protos = torch.randn(text_classes, d, generator=g, device=device)
+        lab = (z % text_classes).to(torch.int32)
+        return x.contiguous(), protos[lab.long()].contiguous(), lab
     if noise > 0:
         order = torch.argsort(z, stable=True)
         counts = torch.bincount(z, minlength=C)
@@ -145,7 +150,7 @@ def cpu_reference_sample(wl, n_queries, seed=1234):
     import torch
     from oracle import lemon_oracle as O
     dev = "cuda" if torch.cuda.is_available() else "cpu"
-    x, y, _ = synth_pairs(wl["n"], wl["d"], wl["noise"], seed, dev)
+    x, y, _ = synth_pairs(wl["n"], wl["d"], wl["noise"], seed, dev, wl.get("text_classes", 0))
     x, y = x.cpu().numpy(), y.cpu().numpy()
     idx = np.arange(wl["n"])
     t0 = time.perf_counter()
@@ -216,7 +221,8 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
 
     n, d, k = wl["n"], wl["d"], wl["k"]
-    x, y, _ = synth_pairs(n, d, wl["noise"], 1234, dev)
+    x, y, lab = synth_pairs(n, d, wl["noise"], 1234, dev, wl.get("text_classes", 0))
+    lab = lab if wl.get("text_classes") else None
     r0, r1, per = ldist.shard_bounds(n, world, rank)
 
     def padded(t):
@@ -224,11 +230,13 @@ def main():
         out[: r1 - r0] = t[r0:r1]
         return out
     img_local, txt_local = padded(x), padded(y)
+    lab_local = padded(lab.view(-1, 1)).view(-1) if lab is not None else None
     del x, y
     scorer = lemon_b200.get_scorer(local_rank)
 
     def step(img, txt):
-        return ldist.score_pairs_sharded(img, txt, n, k=k, dist_type="cosine", hparams=HP, scorer=scorer)
+        return ldist.score_pairs_sharded(img, txt, n, k=k, dist_type="cosine", hparams=HP, scorer=scorer,
+                                         text_label_ids_local=lab_local)
 
     def barrier():
         if world > 1:

@@ -348,7 +348,10 @@ __device__ __forceinline__ void boot_select(const uint64_t* warp_keys, float& th
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
     (void)p3;
     const float th = c0 >= kKeep ? p0 : (c1 >= kKeep ? p1 : (c2 >= kKeep ? p2 : mn));   // mn: all 128 maxima >= it
-    if (lane == L) theta = fmaxf(theta, th);
+    // the filter keeps values STRICTLY above the threshold, and the >= 64 columns that certify `th` are only
+    // collected later (re-scan): step one ulp down so that columns equal to `th` (mass ties!) are kept too
+    const float th_open = __uint_as_float(f2ord_dec(th));
+    if (lane == L) theta = fmaxf(theta, th_open);
   }
 }
 
@@ -372,7 +375,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int64_t n_units = gridDim.x / CG;
   constexpr int kBRows = BN / CG;                  // DB rows this CTA stages per tile
   constexpr uint32_t kStageBytes = kBRows * kBK * 2;
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kTmemCols = 512;              // all of TMEM: kNBuf accumulator buffers of BN columns
+  constexpr uint32_t kNBuf = 512 / BN;             // 2 (BN=256) or 4 (BN=128); buffer b belongs to epilogue group b & 1
   constexpr int kBoot = kBootTiles * 256 / BN;     // bootstrap tiles per item: 128 group maxima per epilogue group
 
   const uint32_t a_smem = smem_base;
@@ -382,18 +386,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.nstage + s); };
   const uint32_t a_full = bar_base + 8u * (2 * p.nstage);
   const uint32_t a_empty = a_full + 8;
-  const uint32_t tmem_full = a_full + 16;    // [2]
-  const uint32_t tmem_empty = a_full + 32;   // [2]
-  const uint32_t tmem_slot = a_full + 48;
+  const uint32_t tmem_full = a_full + 16;    // [4]
+  const uint32_t tmem_empty = a_full + 48;   // [4]
+  const uint32_t tmem_slot = a_full + 80;
   // per-row threshold exchange between the two epilogue groups: [2][128] x (item tag << 32 | float bits)
-  volatile uint64_t* th_sh = reinterpret_cast<volatile uint64_t*>(smem_raw + (a_full + 64 - smem_u32(smem_raw)));
+  volatile uint64_t* th_sh = reinterpret_cast<volatile uint64_t*>(smem_raw + (a_full + 96 - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4); }
+    for (int b = 0; b < int(kNBuf); ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, kTmemCols);
@@ -451,7 +455,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         tc_fence_after();
         const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);
         for (int64_t i = 0; i < nsteps; ++i, ++tc) {
-          const uint32_t buf = tc & 1, use = tc >> 1;
+          const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
           mbar_wait(tmem_empty + 8 * buf, (use & 1) ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
@@ -506,8 +510,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       int bcount = 0;
       for (int64_t i = 0; i < nsteps; ++i, ++tc) {
         const int64_t t = i < ntiles ? i : i - ntiles;
-        const uint32_t buf = tc & 1, use = tc >> 1;
-        if (!one_group && int(buf) != grp) continue;
+        const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
+        if (!one_group && int(buf & 1) != grp) continue;
         mbar_wait(tmem_full + 8 * buf, use & 1);
         tc_fence_after();
         if (i < nboot && bcount >= 0) {
@@ -710,11 +714,11 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
   const uint32_t stage_bytes = (BN / CG) * kBK * 2;
   // dynamic shared memory starts 1024-aligned (no static __shared__ in this kernel; checked on the device)
-  const int64_t avail = int64_t(kMaxSmem) - 2304 /*barriers + threshold exchange*/ - a_bytes;
+  const int64_t avail = int64_t(kMaxSmem) - 2368 /*barriers + threshold exchange*/ - a_bytes;
   int nstage = int(avail / stage_bytes);
   if (nstage > 8) nstage = 8;
   if (nstage < 2) return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: d16=%d leaves no room for a DB ring", d16);
-  const size_t smem = a_bytes + size_t(nstage) * stage_bytes + 2304;
+  const size_t smem = a_bytes + size_t(nstage) * stage_bytes + 2368;
 
   TcParams p;
   p.nq = nq; p.m = m; p.kchunks = kchunks; p.nstage = nstage;
@@ -776,10 +780,16 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
   if (cta_group == 0) cta_group = 2;   // CTA pairs: half the SMEM/L2 operand traffic per MMA
   cudaStream_t st = (cudaStream_t)stream;
   LEMON_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+  const char* bn_env = getenv("LEMON_TC_BN");        // experiments: force the DB tile width (128 or 256)
+  int bn = bn_env ? atoi(bn_env) : 0;
   if (cta_group == 1) {
-    if (d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+    if (bn == 0) bn = d16 <= 512 ? 256 : 128;
+    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
     return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
   }
-  if (cta_group == 2) return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+  if (cta_group == 2) {
+    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+  }
   return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: cta_group must be 0, 1 or 2");
 }

@@ -45,6 +45,11 @@ __device__ __forceinline__ float ord2f(uint32_t o) {
   uint32_t u = o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu);
   return __uint_as_float(u);
 }
+// bit pattern of the largest float strictly below f (f finite, not the most negative float)
+__device__ __forceinline__ uint32_t f2ord_dec(float f) {
+  const uint32_t o = f2ord(f) - 1u;
+  return o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu);
+}
 __device__ __forceinline__ uint64_t make_key(float v, uint32_t idx) {
   return (uint64_t(f2ord(v)) << 32) | uint64_t(~idx);
 }

@@ -327,3 +327,22 @@ def test_results_adapter_feeds_metrics_compat(lb):
     df = results.records_to_dataframe(out, "train", is_mislabel=mis)
     s = metrics_compat.calc_scores_given_hparams_vectorized(df, HP)
     np.testing.assert_allclose(s, out["score"].cpu().numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["ten_classes", "dup25"])
+def test_tc_long_db_with_mass_ties(lb, kind):
+    """DB long enough for K1's threshold bootstrap (>= 64 tiles) and full of exact duplicates: the bootstrap
+    threshold must not lose the tied columns; results equal the fp32 brute-force kernel bit for bit."""
+    if kind == "ten_classes":
+        x, y, lab, _ = clustered_pairs(20000, 128, n_clusters=40, seed=95, dup_text_classes=10)
+        mat = y
+    else:
+        base, _ = iid_pairs(800, 128, seed=96)
+        mat = np.repeat(base, 25, axis=0)[np.random.RandomState(1).permutation(20000)]
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(mat[:600], True), sc.prepare(mat, True)
+    cv, ci, nseg = sc.knn_candidates(qp, dbp)
+    assert bool((ci >= 0).all())                         # 64 real candidates per row, nothing lost
+    tv, ti = sc.knn(qp, dbp, 31, 0, mode="tc")
+    ev, ei = sc.knn(qp, dbp, 31, 0, mode="exact")
+    assert bool((ti == ei).all()) and bool((tv == ev).all())

@@ -138,6 +138,19 @@ int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_
                          const double* d1, int64_t n, int k, const double* hp /* HOST [6] */, double* sn,
                          double* sm, double* score, void* stream);
 
+/* Exact-duplicate DB rows are searched once (classification datasets: C distinct text embeddings; caption noise
+ * duplicates captions).  lemon_hash_rows: 63-bit hash of every row's bit pattern (the caller sorts/groups);
+ * lemon_rows_equal: sets flag[0] |= 1 if a row differs bit-wise from rep_of_row[row] (hash collision check);
+ * lemon_expand_groups: turns top lists over the unique rows (uval/uidx [nq,kp]) into top lists over the original
+ * rows: group u owns members[offsets[u] .. offsets[u+1]) (ascending DB index); entries keep the group's value.
+ */
+int lemon_hash_rows(lemon_ctx* ctx, const float* x, int64_t n, int d, int64_t* out, void* stream);
+int lemon_rows_equal(lemon_ctx* ctx, const float* x, const int64_t* rep_of_row, int64_t n, int d,
+                     int32_t* flag, void* stream);
+int lemon_expand_groups(lemon_ctx* ctx, const float* uval, const int32_t* uidx, const int64_t* offsets,
+                        const int32_t* members, int64_t nq, int kp, int metric, float* top_val,
+                        int32_t* top_idx, void* stream);
+
 /* Number of kernels this library has launched through `ctx` since creation (bench "gpu_launches"). */
 int64_t lemon_launch_count(lemon_ctx* ctx);
 

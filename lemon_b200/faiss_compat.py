@@ -52,6 +52,7 @@ class _IndexFlat:
             allx = self._chunks[0] if len(self._chunks) == 1 else torch.cat(self._chunks)
             self._chunks = [allx]
             self._prepared = self._sc().prepare(allx, normalize=False)
+            self._prepared.dedup = self._sc().find_duplicates(self._prepared)
         return self._prepared
 
     def search(self, x, k: int):
@@ -67,8 +68,6 @@ class _IndexFlat:
         I = torch.full((nq, k), -1, dtype=torch.int64, device=sc.device)
         if self.ntotal > 0 and nq > 0:
             q = sc.prepare(xt, normalize=False)
-            done = 0
-            # top lists hold at most 64 entries; larger k is served in exact passes is not supported
             if k > 64:
                 raise RuntimeError("lemon_b200.faiss_compat: k > 64 is not supported")
             tv, ti = sc.knn(q, self._db(), k, self.metric_type)

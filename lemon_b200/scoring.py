@@ -54,11 +54,22 @@ class Prepared:
     n: int
     d: int
     d16: int
+    dedup: "Dedup | None" = None   # set for databases with many bit-identical rows
+
+
+@dataclass
+class Dedup:
+    """Exact-duplicate structure of a database: the search runs on `uniq` (one representative per group of
+    bit-identical rows, in ascending order of the representative's DB index) and is expanded back."""
+    uniq: "Prepared"
+    offsets: torch.Tensor    # int64 [n_unique + 1]
+    members: torch.Tensor    # int32 [n]: DB rows grouped by unique row, ascending inside a group
+    n_unique: int
 
 
 def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
     return Prepared(p.f32[r0:r1], None if p.f16 is None else p.f16[r0:r1], p.row_stats[r0:r1], p.stats_max,
-                    r1 - r0, p.d, p.d16)
+                    r1 - r0, p.d, p.d16, None)
 
 
 def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512) -> int:
@@ -87,7 +98,7 @@ class LemonScorer:
     ``set_database`` == lines 163-176 (normalise, dists_tr, index.add),
     ``score``        == lines 235-307 for all queries of a split + utils.py:47-82."""
 
-    def __init__(self, device=None, knn_mode: str = "auto", cta_group: int = 0):
+    def __init__(self, device=None, knn_mode: str = "auto", cta_group: int = 0, dedup: bool = True):
         if not torch.cuda.is_available():
             raise _lib.LemonError("lemon_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else
@@ -97,6 +108,7 @@ class LemonScorer:
         assert knn_mode in ("auto", "tc", "exact")
         self.knn_mode = knn_mode
         self.cta_group = cta_group
+        self.dedup = dedup
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.db = None
         self.last_info: dict = {}
@@ -120,6 +132,45 @@ class LemonScorer:
                                                          _ptr(row_stats), _ptr(stats_max), n, d, d16,
                                                          int(bool(normalize)), _stream()), "lemon_normalize_cast")
         return Prepared(out32, out16, row_stats, stats_max, n, d, d16)
+
+    def find_duplicates(self, p: Prepared, min_saving: float = 0.1) -> "Dedup | None":
+        """Groups bit-identical rows (hash -> sort -> bit-wise verification).  Returns None when fewer than
+        `min_saving` of the rows are duplicates, or on a hash collision (then nothing is deduplicated)."""
+        n, dev = p.n, self.device
+        if n < 64:
+            return None
+        h = torch.empty(n, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            self.ctx.check(self.lib.lemon_hash_rows(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(h), _stream()),
+                           "lemon_hash_rows")
+        hs, order = torch.sort(h, stable=True)            # equal hashes keep ascending row index
+        newg = torch.ones(n, dtype=torch.bool, device=dev)
+        newg[1:] = hs[1:] != hs[:-1]
+        n_u = int(newg.sum().item())
+        if n_u > (1.0 - min_saving) * n:
+            return None
+        gid_sorted = torch.cumsum(newg, 0) - 1             # group of every sorted position
+        rep_rows = order[torch.nonzero(newg).flatten()]    # lowest row index of each group
+        rep_of_row = torch.empty(n, dtype=torch.int64, device=dev)
+        rep_of_row[order] = rep_rows[gid_sorted]
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            self.ctx.check(self.lib.lemon_rows_equal(self.ctx.handle, _ptr(p.f32), _ptr(rep_of_row), n, p.d, _ptr(flag),
+                                                     _stream()), "lemon_rows_equal")
+        if int(flag.item()) != 0:
+            return None                                    # 63-bit hash collision: do not deduplicate
+        perm = torch.argsort(rep_rows)                     # renumber groups by ascending representative index
+        inv = torch.empty_like(perm)
+        inv[perm] = torch.arange(n_u, device=dev)
+        new_gid = inv[gid_sorted]
+        o2 = torch.argsort(new_gid, stable=True)           # rows inside a group stay in ascending index order
+        members = order[o2].to(torch.int32).contiguous()
+        offsets = torch.zeros(n_u + 1, dtype=torch.int64, device=dev)
+        offsets[1:] = torch.cumsum(torch.bincount(new_gid, minlength=n_u), 0)
+        rep = rep_rows[perm]
+        uniq = Prepared(p.f32[rep].contiguous(), None if p.f16 is None else p.f16[rep].contiguous(),
+                        p.row_stats[rep].contiguous(), p.stats_max, n_u, p.d, p.d16)
+        return Dedup(uniq, offsets, members, n_u)
 
     def rowwise_dist(self, a: torch.Tensor, b: torch.Tensor, metric: int) -> torch.Tensor:
         out = torch.empty(a.shape[0], dtype=torch.float32, device=self.device)
@@ -183,7 +234,20 @@ class LemonScorer:
         mode = mode or self.knn_mode
         if kp > MAX_KP:
             raise ValueError(f"k (+1) = {kp} exceeds {MAX_KP}")
-        use_tc = mode == "tc" or (mode == "auto" and self.tc_eligible(q, db))
+        if db.dedup is not None:
+            # many identical DB rows: search the unique rows, then expand every hit to its group's members
+            dd = db.dedup
+            uv, ui = self.knn(q, dd.uniq, kp, metric, mode)
+            info = dict(self.last_info, n_unique=dd.n_unique)
+            tv = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
+            ti = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                self.ctx.check(self.lib.lemon_expand_groups(self.ctx.handle, _ptr(uv), _ptr(ui), _ptr(dd.offsets),
+                                                            _ptr(dd.members), q.n, kp, metric, _ptr(tv), _ptr(ti),
+                                                            _stream()), "lemon_expand_groups")
+            self.last_info = info
+            return tv, ti
+        use_tc = mode == "tc" or (mode == "auto" and self.tc_eligible(q, db) and db.n >= 2048)
         if mode == "tc" and not self.tc_eligible(q, db):
             raise _lib.LemonError("tensor-core path not eligible for this shape (padded d must be <= 768)")
         if not use_tc:
@@ -206,6 +270,9 @@ class LemonScorer:
         xdb = self.prepare(img_db, normalize, need16)
         ydb = self.prepare(txt_db, normalize, need16)
         assert xdb.n == ydb.n and xdb.d == ydb.d
+        if self.dedup:
+            xdb.dedup = self.find_duplicates(xdb)
+            ydb.dedup = self.find_duplicates(ydb)
         self.db = {"x": xdb, "y": ydb, "metric": metric, "normalize": normalize,
                    "dists_tr": self.rowwise_dist(ydb.f32, xdb.f32, metric),
                    "labels": _to_dev(text_label_ids_db, self.device, torch.int32)}

@@ -346,3 +346,29 @@ def test_tc_long_db_with_mass_ties(lb, kind):
     tv, ti = sc.knn(qp, dbp, 31, 0, mode="tc")
     ev, ei = sc.knn(qp, dbp, 31, 0, mode="exact")
     assert bool((ti == ei).all()) and bool((tv == ev).all())
+
+
+def test_duplicate_rows_are_searched_once_and_expanded_exactly(lb):
+    """Classification-style DB (10 distinct text rows) and caption-noise duplicates: the deduplicated search
+    returns bit-for-bit what the plain search returns, and both match the oracle."""
+    import torch
+    x, y, lab, _ = clustered_pairs(6000, 128, n_clusters=30, seed=97, dup_text_classes=10)
+    n = 6000
+    plain = lb.LemonScorer(dedup=False)
+    dd = lb.LemonScorer(dedup=True)
+    outs = []
+    for sc in (plain, dd):
+        sc.set_database(x, y, "cosine", True, lab)
+        outs.append(_np(sc.score(None, None, k=30, query_in_db=np.arange(n), hparams=HP, text_label_ids_q=lab,
+                                 queries_are_db=True)))
+    assert dd.db["y"].dedup is not None and dd.db["y"].dedup.n_unique == 10 and dd.db["x"].dedup is None
+    for c in outs[0]:
+        assert (outs[0][c] == outs[1][c]).all(), c
+    check_against_oracle(outs[1], x, y, x, y, k=30, query_in_db=np.arange(n), hparams=HP, lab_q=lab, lab_db=lab)
+    # caption-noise duplicates (pairs / triples of identical rows) on the general path
+    x2, y2, _, _ = clustered_pairs(5000, 512, n_clusters=40, seed=98, noise_frac=0.4)
+    a = _np(plain.set_database(x2, y2).score(None, None, k=10, query_in_db=np.arange(5000), hparams=HP, queries_are_db=True))
+    b = _np(dd.set_database(x2, y2).score(None, None, k=10, query_in_db=np.arange(5000), hparams=HP, queries_are_db=True))
+    assert dd.db["y"].dedup is not None and dd.db["y"].dedup.n_unique < 4600
+    for c in a:
+        assert (a[c] == b[c]).all(), c

@@ -172,6 +172,13 @@ class LemonScorer:
                         p.row_stats[rep].contiguous(), p.stats_max, n_u, p.d, p.d16)
         return Dedup(uniq, offsets, members, n_u)
 
+    def prepare_db(self, x, normalize: bool = True) -> Prepared:
+        """K0 + duplicate detection for one database matrix (run_lemon.py:163-164,175-176)."""
+        p = self.prepare(x, normalize, self.knn_mode != "exact")
+        if self.dedup:
+            p.dedup = self.find_duplicates(p)
+        return p
+
     def rowwise_dist(self, a: torch.Tensor, b: torch.Tensor, metric: int) -> torch.Tensor:
         out = torch.empty(a.shape[0], dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -266,13 +273,9 @@ class LemonScorer:
     def set_database(self, img_db, txt_db, dist_type: str = "cosine", normalize: bool = True,
                      text_label_ids_db=None):
         metric = METRIC[dist_type]
-        need16 = self.knn_mode != "exact"
-        xdb = self.prepare(img_db, normalize, need16)
-        ydb = self.prepare(txt_db, normalize, need16)
+        xdb = self.prepare_db(img_db, normalize)
+        ydb = self.prepare_db(txt_db, normalize)
         assert xdb.n == ydb.n and xdb.d == ydb.d
-        if self.dedup:
-            xdb.dedup = self.find_duplicates(xdb)
-            ydb.dedup = self.find_duplicates(ydb)
         self.db = {"x": xdb, "y": ydb, "metric": metric, "normalize": normalize,
                    "dists_tr": self.rowwise_dist(ydb.f32, xdb.f32, metric),
                    "labels": _to_dev(text_label_ids_db, self.device, torch.int32)}
@@ -318,6 +321,18 @@ class LemonScorer:
         info_n = self.last_info
         topm = self.knn(yq, db["y"], kp, metric)
         info_m = self.last_info
+        out = self.emit(xq, yq, db["x"], db["y"], db["dists_tr"], topn, topm, k=k, kp=kp, metric=metric, qid=qid,
+                        lab_q=lab_q, lab_db=lab_db, cls_emb=cls_emb, lab_noisy=lab_noisy, n_class=n_class,
+                        hparams=hparams, return_records=return_records)
+        self.last_info = {"img": info_n, "txt": info_m}
+        return out
+
+    def emit(self, xq: Prepared, yq: Prepared, xdb: Prepared, ydb: Prepared, dists_tr, topn, topm, *, k: int, kp: int,
+             metric: int, qid=None, lab_q=None, lab_db=None, cls_emb=None, lab_noisy=None, n_class=None,
+             hparams: dict | None = None, return_records: bool = True) -> dict:
+        """K2b: per-sample records + score from exact top lists (run_lemon.py:250-307, utils.py:63-77)."""
+        nq = xq.n
+        db = {"x": xdb, "y": ydb, "dists_tr": dists_tr}
         dev = self.device
         f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         out = {"d_1": f32(nq)}
@@ -339,7 +354,6 @@ class LemonScorer:
                 _ptr(cls_emb), _ptr(lab_noisy), int(n_class or 0), nq, db["x"].n, db["x"].d, k, kp, metric, hp_arr, g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"),
                 g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"), g("s_n"), g("s_m"), g("score"),
                 _stream()), "lemon_score")
-        self.last_info = {"img": info_n, "txt": info_m}
         return out
 
     def combine_scores(self, rec: dict, hparams: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

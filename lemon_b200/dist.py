@@ -23,7 +23,7 @@ def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int, int]:
 def allgather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
     """local: [per, d] (rows past the rank's valid count are padding).  Returns the replicated
     [n_total, d] matrix; padding only ever sits at the tail, so it is sliced off."""
-    world = dist.get_world_size(group)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return local[:n_total]
     per, d = local.shape

@@ -93,12 +93,17 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     # ---- image side (run_lemon.py:164,168/172,176,235) while the text shard may still be copying
     xdb = scorer.prepare_db(allgather_rows(img_local, n_total, group), normalize)
     xq = _slice_prepared(xdb, r0, r1)
+    ydb = None
+    if e_txt is None:
+        # device-resident shards: stage the text side too before the long kernels are queued (duplicate
+        # detection reads two scalars back; doing it now keeps the host ahead of the GPU)
+        ydb = scorer.prepare_db(allgather_rows(txt_local, n_total, group), normalize)
     topn = scorer.knn(xq, xdb, kp, metric)
     info_n = scorer.last_info
     # ---- text side
-    if e_txt is not None:
+    if ydb is None:
         main.wait_event(e_txt)
-    ydb = scorer.prepare_db(allgather_rows(txt_local, n_total, group), normalize)
+        ydb = scorer.prepare_db(allgather_rows(txt_local, n_total, group), normalize)
     yq = _slice_prepared(ydb, r0, r1)
     dtr = scorer.rowwise_dist(ydb.f32, xdb.f32, metric)
     topm = scorer.knn(yq, ydb, kp, metric)

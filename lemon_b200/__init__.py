@@ -9,7 +9,7 @@ Public surface (mirrors the reference's seams):
 """
 from . import _lib
 from ._lib import LemonError, LIB_PATH
-from .scoring import LemonScorer, score_pairs, get_scorer, plan_segments, HP_KEYS
+from .scoring import LemonScorer, score_pairs, get_scorer, plan_segments, plan_tail, HP_KEYS
 
 __all__ = ["LemonScorer", "score_pairs", "get_scorer", "plan_segments", "LemonError", "LIB_PATH", "HP_KEYS",
            "install_faiss_shim", "patch_reference_metrics"]

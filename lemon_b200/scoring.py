@@ -93,6 +93,26 @@ def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512)
     return best
 
 
+def plan_tail(nq: int, m: int, num_sms: int, cta_group: int) -> tuple[int, int]:
+    """Wave-quantisation fix for the tensor-core kernel.  Its work items are 128*cta_group-row query tiles
+    dealt to num_sms/cta_group CTA (pairs); when the last round is mostly empty, the rows of that round are
+    searched by a second launch with the DB split into segments so that every CTA pair gets a (short) item.
+    Returns (rows of the main launch, segments of the tail launch); (nq, 1) means one launch."""
+    units = max(1, num_sms // cta_group)
+    rows_per_tile = 128 * cta_group
+    tiles = -(-nq // rows_per_tile)
+    full = (tiles // units) * units
+    tail = tiles - full
+    if full == 0 or tail == 0 or tail > 0.6 * units:
+        return nq, 1
+    nseg = min(units // tail, 8)
+    while nseg > 1 and m // nseg < 4096:
+        nseg -= 1
+    if nseg <= 1:
+        return nq, 1
+    return full * rows_per_tile, nseg
+
+
 class LemonScorer:
     """Drop-in engine for the scoring path.  Mirrors the order of run_lemon.py:
     ``set_database`` == lines 163-176 (normalise, dists_tr, index.add),
@@ -222,9 +242,11 @@ class LemonScorer:
         return cand_val, cand_idx, nseg
 
     def rerank(self, q: Prepared, db: Prepared, cand_val, cand_idx, nseg: int, kp: int, metric: int,
-               use_bound: bool = True):
-        top_val = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
-        top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
+               use_bound: bool = True, out=None):
+        if out is None:
+            out = (torch.empty((q.n, kp), dtype=torch.float32, device=self.device),
+                   torch.empty((q.n, kp), dtype=torch.int32, device=self.device))
+        top_val, top_idx = out
         uncert = torch.empty(max(q.n, 1), dtype=torch.int32, device=self.device)
         n_unc = torch.zeros(1, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
@@ -261,12 +283,24 @@ class LemonScorer:
             tv, ti = self.knn_exact(q, db, kp, metric)
             self.last_info = {"path": "exact"}
             return tv, ti
-        cand_val, cand_idx, nseg = self.knn_candidates(q, db)
-        top_val, top_idx, uncert, n_unc = self.rerank(q, db, cand_val, cand_idx, nseg, kp, metric)
-        # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the
-        # device, so no host synchronisation is needed here
-        self.knn_exact(q, db, kp, metric, top=(top_val, top_idx), rows=uncert, n_rows=n_unc)
-        self.last_info = {"path": "tc", "nseg": nseg, "n_uncertified": n_unc}
+        top_val = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
+        top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
+        cg = self.cta_group if self.cta_group else 2
+        n_main, nseg_tail = plan_tail(q.n, db.n, self.num_sms, cg)
+        parts = [(0, q.n, None)] if n_main >= q.n else [(0, n_main, 1), (n_main, q.n, nseg_tail)]
+        n_uncs, nsegs = [], []
+        for r0, r1, ns in parts:
+            qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)
+            cand_val, cand_idx, nseg = self.knn_candidates(qs, db, nseg=ns)
+            tv, ti = top_val[r0:r1], top_idx[r0:r1]
+            _, _, uncert, n_unc = self.rerank(qs, db, cand_val, cand_idx, nseg, kp, metric, out=(tv, ti))
+            # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the
+            # device, so no host synchronisation is needed here
+            self.knn_exact(qs, db, kp, metric, top=(tv, ti), rows=uncert, n_rows=n_unc)
+            n_uncs.append(n_unc)
+            nsegs.append(nseg)
+        self.last_info = {"path": "tc", "nseg": nsegs[0] if len(nsegs) == 1 else nsegs,
+                          "n_uncertified": n_uncs[0] if len(n_uncs) == 1 else torch.stack(n_uncs).sum(0)}
         return top_val, top_idx
 
     # ------------------------------------------------- run_lemon.py:163-176

@@ -69,3 +69,15 @@ def test_faiss_shim_installs():
             sys.modules["faiss"] = old
         else:
             sys.modules.pop("faiss", None)
+
+
+def test_plan_tail():
+    from lemon_b200 import plan_tail
+    # C2 on one GPU: 461 pair tiles on 74 pairs = 6 full rounds + 17 tiles -> the 17 go to a 4-segment launch
+    n_main, nseg = plan_tail(118_000, 118_000, 148, 2)
+    assert n_main == 6 * 74 * 256 and nseg == 4
+    assert plan_tail(74 * 256 * 3, 118_000, 148, 2) == (74 * 256 * 3, 1)       # exact multiple: nothing to fix
+    assert plan_tail(1000, 118_000, 148, 2) == (1000, 1)                       # less than one round: plan_segments' job
+    assert plan_tail(74 * 256 + 60 * 256, 118_000, 148, 2)[1] == 1             # tail nearly a full round: leave it
+    n_main, nseg = plan_tail(118_000, 10_000, 148, 2)
+    assert nseg == 2 and 10_000 // nseg >= 4096                                # short DB: fewer segments

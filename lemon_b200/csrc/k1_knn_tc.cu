@@ -608,13 +608,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         prune_rows(warp_keys, cnt, theta, kSoftLimit, kPrunesPerTile, lane, exact_only);
         th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       }
-      // ---- item done: every row's buffer is sorted; group 1 hands its best 64 to group 0, which merges
-      // and emits the best 64 (descending; ties by lower DB index)
+      // ---- item done.  Phase A (both groups, concurrently): every row's buffer is sorted; group 1 writes its
+      // best 64 (reversed) to the hand-off area, group 0 writes its best 64 back to its own buffer.  Phase B
+      // (group 0): bitonic merge of the two sorted lists, emit the best 64 (descending; ties by lower DB index).
       __syncwarp();
-      if (grp == 1 && it > 0 && !(p.debug & 8) && !one_group) named_bar_sync(5 + quad, 64);     // group 0 has consumed the previous hand-off
-      for (int L = 0; L < ((p.debug & 8) ? 0 : 32); ++L) {   // debug 8: skip the item-end merge (timing experiments only)
+      const bool do_end = !(p.debug & 8);        // debug 8: skip the item-end work (timing experiments only)
+      if (grp == 1 && it > 0 && do_end && !one_group) named_bar_sync(5 + quad, 64);   // previous hand-off consumed
+      for (int L = 0; L < (do_end ? 32 : 0); ++L) {
         const int cntL = __shfl_sync(kFull, cnt, L);
-        const int64_t rowL = __shfl_sync(kFull, row, L);
         uint64_t* b = warp_keys + size_t(L) * kCap;
         uint64_t key[8];
 #pragma unroll
@@ -624,49 +625,57 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           key[i + 1] = (lane * 8 + i + 1) < cntL ? tt.y : 0ull;
         }
         warp_sort256_desc(key, lane);
-        if (grp == 1) {
-          if (lane < kKeep / 8) {      // reversed: slot s of the hand-off holds rank 63 - s
+        if (lane < kKeep / 8) {
+          if (grp == 1) {              // reversed: slot s of the hand-off holds rank 63 - s
 #pragma unroll
             for (int i = 0; i < 8; i += 2)
               *reinterpret_cast<ulonglong2*>(handoff + size_t(L) * kKeep + (kKeep - 8 - lane * 8) + (6 - i)) =
                   make_ulonglong2(key[i + 1], key[i]);
-          }
-          continue;
-        }
-        if (L == 0 && !one_group) named_bar_sync(1 + quad, 64);  // group 1's hand-off for this item is complete
-        // lanes 0-7 hold this group's best 64 (descending); lanes 8-15 load the other group's, reversed
-        if (lane >= kKeep / 8) {
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) key[i] = 0ull;
-          if (lane < 2 * (kKeep / 8) && !one_group) {
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(handoff + size_t(L) * kKeep + (lane - kKeep / 8) * 8 + i));
-              key[i] = tt.x; key[i + 1] = tt.y;
-            }
+            for (int i = 0; i < 8; i += 2)
+              *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
           }
-        }
-        warp_merge_best64_desc(key, lane);
-        if (rowL < p.nq && lane < kKeep / 8) {
-          float* ov = p.cand_val + (rowL * p.nseg + seg) * kKeep + lane * 8;
-          int32_t* oi = p.cand_idx + (rowL * p.nseg + seg) * kKeep + lane * 8;
-          float fv[8]; int32_t iv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const bool ok = key[i] != 0ull;
-            fv[i] = ok ? key_val(key[i]) : -CUDART_INF_F;
-            iv[i] = ok ? key_idx(key[i]) : -1;
-          }
-          *reinterpret_cast<float4*>(ov) = make_float4(fv[0], fv[1], fv[2], fv[3]);
-          *reinterpret_cast<float4*>(ov + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
-          *reinterpret_cast<int4*>(oi) = make_int4(iv[0], iv[1], iv[2], iv[3]);
-          *reinterpret_cast<int4*>(oi + 4) = make_int4(iv[4], iv[5], iv[6], iv[7]);
         }
       }
       __syncwarp();
-      if (!(p.debug & 8) && !one_group) {
-        if (grp == 1) named_bar_arrive(1 + quad, 64);             // hand-off written (bar orders the global stores)
-        else named_bar_arrive(5 + quad, 64);                      // hand-off consumed
+      if (do_end && grp == 1 && !one_group) named_bar_arrive(1 + quad, 64);   // hand-off written (bar orders the stores)
+      if (do_end && grp == 0) {
+        if (!one_group) named_bar_sync(1 + quad, 64);                         // group 1's hand-off is complete
+        for (int L = 0; L < 32; ++L) {
+          const int64_t rowL = __shfl_sync(kFull, row, L);
+          uint64_t key[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) key[i] = 0ull;
+          const uint64_t* src = nullptr;
+          if (lane < kKeep / 8) src = warp_keys + size_t(L) * kCap + lane * 8;                        // own best 64
+          else if (lane < 2 * (kKeep / 8) && !one_group) src = handoff + size_t(L) * kKeep + (lane - kKeep / 8) * 8;
+          if (src) {
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(src + i));
+              key[i] = tt.x; key[i + 1] = tt.y;
+            }
+          }
+          warp_merge_best64_desc(key, lane);
+          if (rowL < p.nq && lane < kKeep / 8) {
+            float* ov = p.cand_val + (rowL * p.nseg + seg) * kKeep + lane * 8;
+            int32_t* oi = p.cand_idx + (rowL * p.nseg + seg) * kKeep + lane * 8;
+            float fv[8]; int32_t iv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const bool ok = key[i] != 0ull;
+              fv[i] = ok ? key_val(key[i]) : -CUDART_INF_F;
+              iv[i] = ok ? key_idx(key[i]) : -1;
+            }
+            *reinterpret_cast<float4*>(ov) = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            *reinterpret_cast<float4*>(ov + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
+            *reinterpret_cast<int4*>(oi) = make_int4(iv[0], iv[1], iv[2], iv[3]);
+            *reinterpret_cast<int4*>(oi + 4) = make_int4(iv[4], iv[5], iv[6], iv[7]);
+          }
+        }
+        __syncwarp();
+        if (!one_group) named_bar_arrive(5 + quad, 64);                       // hand-off consumed
       }
     }
     }   // !(one_group && grp == 1)

@@ -46,7 +46,8 @@ enum lemon_status {
 
 enum lemon_metric { LEMON_METRIC_IP = 0, LEMON_METRIC_L2 = 1 };
 
-#define LEMON_KPRIME 64          /* candidates kept per (row, DB segment) by the tensor-core kernel */
+#define LEMON_KPRIME 64          /* a row's candidate lists together hold its 64 best approximate values */
+#define LEMON_LIST_CAP 256       /* slots per candidate list */
 #define LEMON_MAX_KP 64          /* largest k (+1 for self-exclusion) a top list can hold */
 #define LEMON_MAX_D_TC 768       /* largest padded dim the tensor-core kernel keeps resident */
 
@@ -71,33 +72,41 @@ int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* 
 int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* out,
                        int64_t n, int d, int metric, void* stream);
 
-/* Tensor-core candidate search (K1): fp16 operands, fp32 TMEM accumulation, streaming top-64
- * fused into the epilogue; the nq x m similarity matrix never reaches HBM.
+/* Tensor-core candidate search (K1): fp16 operands, fp32 TMEM accumulation, streaming top-k fused into the
+ * epilogue; the nq x m similarity matrix never reaches HBM.
  *   q16  [nq, d16], db16 [m, d16]  fp16 row-major, d16 % 64 == 0, d16 <= LEMON_MAX_D_TC
  *   nseg  number of DB segments scanned independently (load balance for small nq); >= 1
- *   cand_val / cand_idx [nq, nseg * LEMON_KPRIME]: per segment the 64 best approximate inner
- *   products, sorted descending (ties: lower DB index first); -inf / -1 padding.
+ *   Output = LEMON_NLIST(nseg) = nseg * 2 candidate lists per query row (two epilogue warp groups per segment).
+ *   nq_pad = nq rounded up to a multiple of 256 rows; the caller allocates all three arrays for nq_pad rows:
+ *     cand_keys  [nq_pad, nseg*2, 256] uint64: key = (order-preserving bits of the approximate inner product) << 32
+ *                | ~db_row; only the first cand_cnt entries of a list are valid, in no particular order;
+ *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. 256);
+ *     cand_theta [nq_pad, nseg*2] fp32: every DB column of that list's share of the scan that is NOT in the list
+ *                has approximate inner product <= theta (-inf: the list holds everything it saw).
+ *   Together the lists of a row contain its 64 best approximate inner products (ties: lower DB rows first).
  *   cta_group: 1 or 2 (2 = cta_group::2 CTA pairs, 256 query rows per pair); 0 = library default.
  */
 int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
-                         int d16, int nseg, int cta_group, float* cand_val, int32_t* cand_idx,
-                         void* stream);
+                         int d16, int nseg, int cta_group, uint64_t* cand_keys, int32_t* cand_cnt,
+                         float* cand_theta, void* stream);
 
 /* fp32 exact re-rank of the candidates + per-row certificate (K2a).
- *   q [nq, d], db [m, d] fp32;  cand_* [nq, ncand] from lemon_knn_candidates (ncand = nseg*64)
+ *   q [nq, d], db [m, d] fp32;  cand_* from lemon_knn_candidates with nlist = nseg*2 lists per row.
+ *   The kernel first selects the row's 64 best approximate candidates over the union of its lists, drops those
+ *   that provably cannot be in the exact top-kp, gathers the rest and evaluates them exactly in fp32.
  *   q_row_stats [nq,4], db_stats_max [4]: outputs of lemon_normalize_cast for the query rows and the DB.
  *   They give the rigorous per-row bound on |fp16 tensor-core inner product - exact|:
  *     eps_row = ||q - q16|| * max||b16|| + ||q|| * max||b - b16|| + acc_eps
  *   (Cauchy-Schwarz on the two rounding-error vectors; acc_eps covers fp32 accumulation).  NULL = eps 0.
  *   Metric L2 ranks by -||q-b||^2 = 2<q,b> - ||q||^2 - ||b||^2; the bound then uses ||q||^2 from
  *   q_row_stats and min||b||^2 >= 1 - db_stats_max[3].
- *   top_val / top_idx [nq, kp]: exact top list.  A row is certified when its kp-th exact value
- *   beats every non-candidate's bound (each segment's 64th approximate value + eps_row); otherwise its
- *   row id is appended to uncert_rows[0 .. *n_uncert) (caller zeroes *n_uncert; room for nq ids).
+ *   top_val / top_idx [nq, kp]: exact top list.  A row is certified when its kp-th exact value beats every
+ *   non-candidate's bound (max over lists of cand_theta, + eps_row); otherwise its row id is appended to
+ *   uncert_rows[0 .. *n_uncert) (caller zeroes *n_uncert; room for nq ids).
  */
-int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const float* cand_val,
-                 const int32_t* cand_idx, const float* q_row_stats, const float* db_stats_max,
-                 float acc_eps, int64_t nq, int64_t m, int d, int ncand, int nseg, int kp,
+int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const uint64_t* cand_keys,
+                 const int32_t* cand_cnt, const float* cand_theta, const float* q_row_stats,
+                 const float* db_stats_max, float acc_eps, int64_t nq, int64_t m, int d, int nlist, int kp,
                  int metric, float* top_val, int32_t* top_idx, int32_t* uncert_rows,
                  int32_t* n_uncert, void* stream);
 

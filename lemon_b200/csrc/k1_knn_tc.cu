@@ -33,9 +33,9 @@ struct TcParams {
   int64_t seg_len;      // columns per segment (multiple of BN)
   int nstage;
   int64_t n_items;      // row_tiles * nseg
-  float* cand_val;
-  int32_t* cand_idx;
-  uint64_t* scratch;    // [gridDim.x] x kScratchPerCta bytes (key buffers + staged groups)
+  uint64_t* cand_keys;  // [nq_pad][nseg][2][kCap]: the streaming key buffers ARE the output
+  int32_t* cand_cnt;    // [nq_pad][nseg][2]
+  float* cand_theta;    // [nq_pad][nseg][2]: every column not in the list has approximate value <= theta
   int debug;            // LEMON_TC_DEBUG bits: 1 = epilogue does no work, 2 = filter only, 4 = exact-sort compaction
 };
 
@@ -199,9 +199,6 @@ constexpr int kPrunesPerTile = 3;
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
 constexpr int kBootMinTiles = 64;              // items shorter than this run without the bootstrap
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g owns TMEM accumulator buffer g
-constexpr size_t kKeysPerGroup = size_t(kBM) * kCap;               // uint64 per (CTA, group)
-constexpr size_t kHandoffPerCta = size_t(kBM) * kKeep;             // uint64: group 1 -> group 0 at item end
-constexpr size_t kScratchPerCta = (kEpiGroups * kKeysPerGroup + kHandoffPerCta) * 8;   // 576 KB
 
 // Prunes one row's key buffer `b` (cntL valid keys; all lanes pass the same arguments).  Fast path: a
 // pivot is picked from a sorted systematic sample of the buffer (every 8th slot) such that at least 64
@@ -259,22 +256,22 @@ __device__ __forceinline__ void prune_one(uint64_t* b, const ulonglong2 (&raw)[4
 
 // Prunes the buffers of (at most max_rows of) the lanes whose key count passed `limit`.  The next row's
 // keys are fetched from L2 while the current row is processed.
-__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, int& cnt, float& theta, int limit, int max_rows,
-                                           int lane, bool exact_only) {
+__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, size_t row_stride, int& cnt, float& theta, int limit,
+                                           int max_rows, int lane, bool exact_only) {
   unsigned need = __ballot_sync(kFull, cnt > limit);
   if (!need) return;
   ulonglong2 raw[4];
-  load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * kCap, raw, lane);
+  load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * row_stride, raw, lane);
   while (need && max_rows-- > 0) {
     const int L = __ffs(need) - 1;
     need &= need - 1;
     ulonglong2 cur[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) cur[i] = raw[i];
-    if (need && max_rows > 0) load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * kCap, raw, lane);
+    if (need && max_rows > 0) load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * row_stride, raw, lane);
     int cntL = __shfl_sync(kFull, cnt, L);
     float thL = __shfl_sync(kFull, theta, L);
-    prune_one(warp_keys + size_t(L) * kCap, cur, cntL, thL, lane, exact_only);
+    prune_one(warp_keys + size_t(L) * row_stride, cur, cntL, thL, lane, exact_only);
     if (lane == L) { cnt = cntL; theta = thL; }
   }
   __syncwarp();
@@ -333,9 +330,9 @@ __device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
 // column, so a value with at least 64 recorded maxima >= it is a valid threshold (at least 64 columns beat it),
 // and it is nearly as tight as the true 64th best of those tiles.  The pivot comes from a sorted sample with
 // an exact count, as in prune_one.  The bootstrap tiles are re-scanned at the end of the item.
-__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, float& theta, int lane) {
+__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, float& theta, int lane) {
   for (int L = 0; L < 32; ++L) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(warp_keys + size_t(L) * kCap) + lane);
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(warp_keys + size_t(L) * row_stride) + lane);
     const float s = warp_sort32_desc_f(v.x, lane);
     const float p0 = __shfl_sync(kFull, s, 13), p1 = __shfl_sync(kFull, s, 16), p2 = __shfl_sync(kFull, s, 20);
     const float p3 = __shfl_sync(kFull, s, 31);
@@ -483,15 +480,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // group is a valid filter for both).  At the end of an item group 1 hands its best 64 per row to
     // group 0, which merges and writes the candidates.
     const int grp = (warp - 4) >> 2;
-    const bool one_group = (p.debug & 32) != 0;     // experiment: a single epilogue group consumes every tile
+    const bool one_group = false;
     if (!(one_group && grp == 1)) {
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
-    uint64_t* cta_scratch = p.scratch + size_t(blockIdx.x) * (kScratchPerCta / 8);
-    uint64_t* warp_keys = cta_scratch + size_t(grp) * kKeysPerGroup + size_t(quad) * 32 * kCap;
-    uint64_t* my_keys = warp_keys + size_t(lane) * kCap;
-    uint64_t* handoff = cta_scratch + kEpiGroups * kKeysPerGroup + size_t(quad) * 32 * kKeep;   // this quadrant's rows
+    const size_t row_stride = size_t(p.nseg) * kEpiGroups * kCap;     // keys between consecutive query rows
     const bool exact_only = (p.debug & 4) != 0;
     const uint32_t tempty0 = (CG == 2) ? mapa_rank0(tmem_empty) : tmem_empty;
     uint32_t tc = 0, it = 0;
@@ -504,6 +498,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint64_t tag = uint64_t(uint32_t(item) + 1u) << 32;
       float theta = (p.debug & 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
+      // this item's key buffers live in the output array: row-major [row][seg][group][kCap]
+      uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kCap) +
+                            size_t(grp) * kCap;
+      uint64_t* my_keys = warp_keys + size_t(lane) * row_stride;
       th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       const int nboot = ntiles >= kBootMinTiles ? kBoot : 0;
       const int64_t nsteps = ntiles + nboot;
@@ -540,7 +538,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
           }
           if (bcount * (BN / 8) >= 128) {   // (single-group mode records 8 tiles but uses the first 4)            // 128 maxima recorded (4 tiles of 256 columns): set the thresholds
-            boot_select(warp_keys, theta, lane);
+            boot_select(warp_keys, row_stride, theta, lane);
             __syncwarp();
             th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
             bcount = -1000000;
@@ -592,7 +590,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               }
             }
             __syncwarp();
-            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow
+            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, row_stride, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow
           }
         }
         // publish this row's threshold and hand the accumulator buffer back to the MMA warp
@@ -605,78 +603,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         // deferred, rate-limited pruning: the accumulator buffer is already released, and at most a few rows
         // are pruned per tile so that the correlated fill of the 32 rows does not turn into one long stall
-        prune_rows(warp_keys, cnt, theta, kSoftLimit, kPrunesPerTile, lane, exact_only);
+        prune_rows(warp_keys, row_stride, cnt, theta, kSoftLimit, kPrunesPerTile, lane, exact_only);
         th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       }
-      // ---- item done.  Phase A (both groups, concurrently): every row's buffer is sorted; group 1 writes its
-      // best 64 (reversed) to the hand-off area, group 0 writes its best 64 back to its own buffer.  Phase B
-      // (group 0): bitonic merge of the two sorted lists, emit the best 64 (descending; ties by lower DB index).
-      __syncwarp();
-      const bool do_end = !(p.debug & 8);        // debug 8: skip the item-end work (timing experiments only)
-      if (grp == 1 && it > 0 && do_end && !one_group) named_bar_sync(5 + quad, 64);   // previous hand-off consumed
-      for (int L = 0; L < (do_end ? 32 : 0); ++L) {
-        const int cntL = __shfl_sync(kFull, cnt, L);
-        uint64_t* b = warp_keys + size_t(L) * kCap;
-        uint64_t key[8];
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + i));
-          key[i] = (lane * 8 + i) < cntL ? tt.x : 0ull;
-          key[i + 1] = (lane * 8 + i + 1) < cntL ? tt.y : 0ull;
-        }
-        warp_sort256_desc(key, lane);
-        if (lane < kKeep / 8) {
-          if (grp == 1) {              // reversed: slot s of the hand-off holds rank 63 - s
-#pragma unroll
-            for (int i = 0; i < 8; i += 2)
-              *reinterpret_cast<ulonglong2*>(handoff + size_t(L) * kKeep + (kKeep - 8 - lane * 8) + (6 - i)) =
-                  make_ulonglong2(key[i + 1], key[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; i += 2)
-              *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
-          }
-        }
+      // ---- item done: the row's key buffer already sits in the output; publish its length and threshold.
+      // (The exact top-64 selection over the union of the lists happens in the re-rank kernel, where thousands
+      // of warps hide its latency; here it would sit on the critical path of one persistent warp.)
+      {
+        const size_t li = (size_t(row) * p.nseg + seg) * kEpiGroups + grp;
+        p.cand_cnt[li] = cnt;
+        p.cand_theta[li] = theta;
       }
       __syncwarp();
-      if (do_end && grp == 1 && !one_group) named_bar_arrive(1 + quad, 64);   // hand-off written (bar orders the stores)
-      if (do_end && grp == 0) {
-        if (!one_group) named_bar_sync(1 + quad, 64);                         // group 1's hand-off is complete
-        for (int L = 0; L < 32; ++L) {
-          const int64_t rowL = __shfl_sync(kFull, row, L);
-          uint64_t key[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) key[i] = 0ull;
-          const uint64_t* src = nullptr;
-          if (lane < kKeep / 8) src = warp_keys + size_t(L) * kCap + lane * 8;                        // own best 64
-          else if (lane < 2 * (kKeep / 8) && !one_group) src = handoff + size_t(L) * kKeep + (lane - kKeep / 8) * 8;
-          if (src) {
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-              const ulonglong2 tt = __ldcg(reinterpret_cast<const ulonglong2*>(src + i));
-              key[i] = tt.x; key[i + 1] = tt.y;
-            }
-          }
-          warp_merge_best64_desc(key, lane);
-          if (rowL < p.nq && lane < kKeep / 8) {
-            float* ov = p.cand_val + (rowL * p.nseg + seg) * kKeep + lane * 8;
-            int32_t* oi = p.cand_idx + (rowL * p.nseg + seg) * kKeep + lane * 8;
-            float fv[8]; int32_t iv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const bool ok = key[i] != 0ull;
-              fv[i] = ok ? key_val(key[i]) : -CUDART_INF_F;
-              iv[i] = ok ? key_idx(key[i]) : -1;
-            }
-            *reinterpret_cast<float4*>(ov) = make_float4(fv[0], fv[1], fv[2], fv[3]);
-            *reinterpret_cast<float4*>(ov + 4) = make_float4(fv[4], fv[5], fv[6], fv[7]);
-            *reinterpret_cast<int4*>(oi) = make_int4(iv[0], iv[1], iv[2], iv[3]);
-            *reinterpret_cast<int4*>(oi + 4) = make_int4(iv[4], iv[5], iv[6], iv[7]);
-          }
-        }
-        __syncwarp();
-        if (!one_group) named_bar_arrive(5 + quad, 64);                       // hand-off consumed
-      }
     }
     }   // !(one_group && grp == 1)
   }
@@ -718,7 +656,7 @@ static int make_map(lemon_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
 
 template <int CG, int BN>
 static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg,
-                     float* cand_val, int32_t* cand_idx, cudaStream_t stream) {
+                     uint64_t* cand_keys, int32_t* cand_cnt, float* cand_theta, cudaStream_t stream) {
   const int kchunks = d16 / kBK;
   const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
   const uint32_t stage_bytes = (BN / CG) * kBK * 2;
@@ -737,22 +675,13 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   p.nseg = nseg; p.seg_len = seg_len;
   const int64_t row_tiles = (nq + kBM * CG - 1) / (kBM * CG);
   p.n_items = row_tiles * nseg;
-  p.cand_val = cand_val; p.cand_idx = cand_idx;
+  p.cand_keys = cand_keys; p.cand_cnt = cand_cnt; p.cand_theta = cand_theta;
   const char* dbg = getenv("LEMON_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
 
   int64_t units = ctx->num_sms / CG;
   if (units > p.n_items) units = p.n_items;
   const unsigned grid = unsigned(units * CG);
-  const size_t need = size_t(ctx->num_sms) * kScratchPerCta;
-  if (ctx->tc_scratch_bytes < need) {
-    if (ctx->tc_scratch) LEMON_CUDA_CHECK(ctx, cudaFree(ctx->tc_scratch));
-    ctx->tc_scratch = nullptr; ctx->tc_scratch_bytes = 0;
-    LEMON_CUDA_CHECK(ctx, cudaMalloc(&ctx->tc_scratch, need));
-    ctx->tc_scratch_bytes = need;
-  }
-  p.scratch = reinterpret_cast<uint64_t*>(ctx->tc_scratch);
-
   CUtensorMap map_q, map_db;
   int rc = make_map(ctx, &map_q, q16, nq, d16, kBM);
   if (rc) return rc;
@@ -778,11 +707,11 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
 }  // namespace lemon
 
 extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
-                                    int d16, int nseg, int cta_group, float* cand_val, int32_t* cand_idx,
-                                    void* stream) {
+                                    int d16, int nseg, int cta_group, uint64_t* cand_keys, int32_t* cand_cnt,
+                                    float* cand_theta, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
-  if (!q16 || !db16 || !cand_val || !cand_idx || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
+  if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
       nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands)", LEMON_MAX_D_TC);
   if (nq == 0) return LEMON_OK;
@@ -793,12 +722,12 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
   int bn = bn_env ? atoi(bn_env) : 0;
   if (cta_group == 1) {
     if (bn == 0) bn = d16 <= 512 ? 256 : 128;
-    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
-    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
   }
   if (cta_group == 2) {
-    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
-    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_val, cand_idx, st);
+    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
   }
   return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: cta_group must be 0, 1 or 2");
 }

@@ -17,6 +17,7 @@ from . import _lib
 
 HP_KEYS = ("beta", "gamma", "tau_1_n", "tau_2_n", "tau_1_m", "tau_2_m")
 KPRIME = 64
+LIST_CAP = 256
 MAX_KP = 64
 MAX_D_TC = 768
 # bound on the fp32 accumulation error of the tensor-core inner product (|q|,|b| <= ~1);
@@ -65,6 +66,25 @@ class Dedup:
     offsets: torch.Tensor    # int64 [n_unique + 1]
     members: torch.Tensor    # int32 [n]: DB rows grouped by unique row, ascending inside a group
     n_unique: int
+
+
+def decode_candidates(cand_keys: torch.Tensor, cand_cnt: torch.Tensor, n_rows: int):
+    """Host-side view of K1's output for tests/debugging: per row the valid (value, db_row) pairs of all lists,
+    sorted by value descending then row ascending.  Returns (vals float32 [n, L], idx int64 [n, L]) padded with
+    (-inf, -1)."""
+    k = cand_keys[:n_rows].cpu().numpy().view(np.uint64)
+    c = cand_cnt[:n_rows].cpu().numpy()
+    n, nlist, cap = k.shape
+    valid = np.arange(cap)[None, None, :] < c[:, :, None]
+    hi = (k >> np.uint64(32)).astype(np.uint32)
+    lo = (k & np.uint64(0xffffffff)).astype(np.uint32)
+    bits = np.where(hi >> 31, hi ^ np.uint32(0x80000000), ~hi)
+    vals = bits.view(np.float32).astype(np.float32)
+    idx = (~lo).astype(np.int64)
+    vals = np.where(valid, vals, -np.inf).reshape(n, -1)
+    idx = np.where(valid, idx, -1).reshape(n, -1)
+    order = np.lexsort((idx, -vals), axis=1)
+    return np.take_along_axis(vals, order, 1), np.take_along_axis(idx, order, 1)
 
 
 def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
@@ -223,26 +243,32 @@ class LemonScorer:
         return top
 
     def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None):
+        """K1.  Returns (cand_keys int64[nq_pad, nlist, 256] (uint64 bit patterns), cand_cnt int32[nq_pad, nlist],
+        cand_theta fp32[nq_pad, nlist], nseg) with nlist = 2*nseg; see include/lemon_b200.h."""
         cg = self.cta_group if cta_group is None else cta_group
         if nseg is None:
             nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2, db.d16)
-        cand_val = torch.empty((q.n, nseg * KPRIME), dtype=torch.float32, device=self.device)
-        cand_idx = torch.empty((q.n, nseg * KPRIME), dtype=torch.int32, device=self.device)
+        nlist = 2 * nseg
+        nq_pad = -(-q.n // 256) * 256
+        cand_keys = torch.empty((nq_pad, nlist, LIST_CAP), dtype=torch.int64, device=self.device)
+        cand_cnt = torch.empty((nq_pad, nlist), dtype=torch.int32, device=self.device)
+        cand_theta = torch.empty((nq_pad, nlist), dtype=torch.float32, device=self.device)
         ev = None
         if self.k1_events is not None:      # bench.py: per-launch device time of the dominant kernel
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_knn_candidates(self.ctx.handle, _ptr(q.f16), _ptr(db.f16), q.n, db.n, db.d16,
-                                                         nseg, cg, _ptr(cand_val), _ptr(cand_idx), _stream()),
-                           "lemon_knn_candidates")
+                                                         nseg, cg, _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
+                                                         _stream()), "lemon_knn_candidates")
         if ev is not None:
             ev[1].record()
             self.k1_events.append((ev[0], ev[1], 2.0 * q.n * db.n * db.d))
-        return cand_val, cand_idx, nseg
+        return cand_keys, cand_cnt, cand_theta, nseg
 
-    def rerank(self, q: Prepared, db: Prepared, cand_val, cand_idx, nseg: int, kp: int, metric: int,
-               use_bound: bool = True, out=None):
+    def rerank(self, q: Prepared, db: Prepared, cand, kp: int, metric: int, use_bound: bool = True, out=None):
+        """K2a on the output of knn_candidates (`cand` = its first three return values)."""
+        cand_keys, cand_cnt, cand_theta = cand
         if out is None:
             out = (torch.empty((q.n, kp), dtype=torch.float32, device=self.device),
                    torch.empty((q.n, kp), dtype=torch.int32, device=self.device))
@@ -251,9 +277,9 @@ class LemonScorer:
         n_unc = torch.zeros(1, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_rerank(
-                self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(cand_val), _ptr(cand_idx),
+                self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
                 _ptr(q.row_stats) if use_bound else None, _ptr(db.stats_max) if use_bound else None,
-                C.c_float(ACC_EPS), q.n, db.n, db.d, cand_val.shape[1], nseg, kp, metric, _ptr(top_val), _ptr(top_idx),
+                C.c_float(ACC_EPS), q.n, db.n, db.d, cand_cnt.shape[1], kp, metric, _ptr(top_val), _ptr(top_idx),
                 _ptr(uncert), _ptr(n_unc), _stream()), "lemon_rerank")
         return top_val, top_idx, uncert, n_unc
 
@@ -291,9 +317,9 @@ class LemonScorer:
         n_uncs, nsegs = [], []
         for r0, r1, ns in parts:
             qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)
-            cand_val, cand_idx, nseg = self.knn_candidates(qs, db, nseg=ns)
+            *cand, nseg = self.knn_candidates(qs, db, nseg=ns)
             tv, ti = top_val[r0:r1], top_idx[r0:r1]
-            _, _, uncert, n_unc = self.rerank(qs, db, cand_val, cand_idx, nseg, kp, metric, out=(tv, ti))
+            _, _, uncert, n_unc = self.rerank(qs, db, cand, kp, metric, out=(tv, ti))
             # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the
             # device, so no host synchronisation is needed here
             self.knn_exact(qs, db, kp, metric, top=(tv, ti), rows=uncert, n_rows=n_unc)

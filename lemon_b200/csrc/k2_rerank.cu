@@ -8,19 +8,22 @@ namespace lemon {
 
 constexpr int kRrWarps = 8;
 
-// sorts the warp's 256-slot shared buffer (cnt valid keys) descending and keeps the best `keep`
-__device__ __forceinline__ void sort_keep(uint64_t* buf, int& cnt, int keep, int lane, uint64_t (&key)[8]) {
-  __syncwarp();
+// loads one chunk = two candidate lists (<= 2 x 256 keys, 16 per lane); invalid slots become 0
+__device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_keys, const int32_t* __restrict__ cand_cnt,
+                                           int64_t row, int nlist, int chunk, int lane, uint64_t (&k)[16], int& tot) {
+  tot = 0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { const int e = lane * 8 + i; key[i] = e < cnt ? buf[e] : 0ull; }
-  warp_sort256_desc(key, lane);
-  __syncwarp();
-  if (lane < keep / 8) {
+  for (int h = 0; h < 2; ++h) {
+    const int l = chunk * 2 + h;
+    const int c = l < nlist ? min(cand_cnt[row * nlist + l], kCap) : 0;
+    tot += c;
+    const uint64_t* src = cand_keys + (row * nlist + (l < nlist ? l : 0)) * kCap;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) buf[lane * 8 + i] = key[i];
+    for (int i = 0; i < 8; ++i) {
+      const int e = i * 32 + lane;                    // coalesced: consecutive lanes read consecutive keys
+      k[h * 8 + i] = e < c ? __ldg(src + e) : 0ull;
+    }
   }
-  cnt = min(cnt, keep);
-  __syncwarp();
 }
 
 template <int METRIC>
@@ -31,35 +34,15 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
               int64_t m, int d, int nlist, int kp, float* __restrict__ top_val, int32_t* __restrict__ top_idx,
               int32_t* __restrict__ uncert_rows, int32_t* __restrict__ n_uncert) {
   __shared__ uint64_t sbuf[kRrWarps][kCap];
-  __shared__ uint64_t sbuf2[kRrWarps][kKeep];
+  __shared__ uint64_t sbuf2[kRrWarps][kCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* buf = sbuf[warp];
-  uint64_t* ebuf = sbuf2[warp];
+  uint64_t* ebuf = sbuf[warp];
+  uint64_t* cbuf = sbuf2[warp];
   const int64_t warps = int64_t(gridDim.x) * kRrWarps;
+  const int nchunk = (nlist + 1) >> 1;
   for (int64_t row = int64_t(blockIdx.x) * kRrWarps + warp; row < nq; row += warps) {
     const float* qr = q + row * d;
-    uint64_t key[8];
-    // ---- 1. the row's 64 best approximate candidates over the union of its lists, and the bound B on every
-    //         column that is in no list (max of the lists' thresholds)
-    int cnt = 0, total = 0;
-    float B = -CUDART_INF_F;
-    for (int l = 0; l < nlist; ++l) {
-      const int c = min(cand_cnt[row * nlist + l], kCap);
-      total += c;
-      B = fmaxf(B, cand_theta[row * nlist + l]);
-      const uint64_t* src = cand_keys + (row * nlist + l) * kCap;
-      for (int off = 0; off < c; off += 32) {
-        if (cnt > kCap - 32) sort_keep(buf, cnt, kKeep, lane, key);
-        const int n = min(32, c - off);
-        if (lane < n) buf[cnt + lane] = __ldg(src + off + lane);
-        cnt += n;
-      }
-    }
-    sort_keep(buf, cnt, kKeep, lane, key);      // buf[0 .. cnt) = best approximate candidates, descending
-    if (total > kKeep) B = fmaxf(B, key_val(buf[kKeep - 1]));   // candidates dropped here are non-candidates too
-    // ---- 2. rounding-error bound of this row (include/lemon_b200.h) and the candidate cut-off: the kp best
-    //         approximate values certify kp elements with exact value >= a_(kp) - eps, so a candidate whose
-    //         approximate value is below a_(kp) - 2 eps cannot be in the exact top-kp and is not gathered
+    // rounding-error bound of this row (include/lemon_b200.h)
     float eps = 0.f, qsq = 1.f, dbdev = 0.f;
     if (q_row_stats) {
       const float4 st = reinterpret_cast<const float4*>(q_row_stats)[row];   // {||q||, ||q16||, ||q-q16||, ||q||^2}
@@ -67,25 +50,79 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
       qsq = st.w;
       dbdev = db_stats_max[3];
     }
-    const float akp = cnt >= kp ? key_val(buf[kp - 1]) : -CUDART_INF_F;
-    const float cut = akp - 2.f * eps - (METRIC == LEMON_METRIC_L2 ? dbdev : 0.f);
-    // ---- 3. exact fp32 values of the surviving candidates
-    int ecnt = 0;
-    for (int t = 0; t < cnt; ++t) {
-      const uint64_t ck = buf[t];                                   // warp-uniform (shared memory broadcast)
-      if (key_val(ck) < cut) break;                                 // sorted: everything after is below the cut too
-      const int idx = key_idx(ck);
-      if (idx < 0 || int64_t(idx) >= m) continue;
-      float v = warp_pair_value<METRIC>(qr, db + int64_t(idx) * d, d, lane);
-      if (METRIC == LEMON_METRIC_L2) v = -v;
-      if (lane == 0) ebuf[ecnt] = make_key(v, uint32_t(idx));
-      ecnt++;
+    // ---- 1. B = bound on every column that is in no list; lb = a lower bound of the kp-th best approximate
+    //         value: a value with at least kp candidates >= it, found by bisection on the ordered bit pattern
+    float B = -CUDART_INF_F;
+    for (int l = lane; l < nlist; l += 32) B = fmaxf(B, cand_theta[row * nlist + l]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) B = fmaxf(B, __shfl_xor_sync(kFull, B, o));
+    uint32_t lb = 0u;                                   // ordered bits; 0 is below every real value
+    uint64_t k[16];
+    int tot;
+    for (int c = 0; c < nchunk; ++c) {
+      load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
+      if (tot < kp) continue;
+      uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const uint32_t o = uint32_t(k[i] >> 32);
+        if (k[i] != 0ull) { lo = min(lo, o); hi = max(hi, o); }
+      }
+      lo = __reduce_min_sync(kFull, lo);
+      hi = __reduce_max_sync(kFull, hi);               // count(>= lo) = tot >= kp ; count(>= hi + 1) = 0
+      for (int it = 0; it < 12 && hi > lo; ++it) {
+        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+        int cge = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cge += (k[i] != 0ull) && (uint32_t(k[i] >> 32) >= mid);
+        cge = __reduce_add_sync(kFull, cge);
+        if (cge >= kp) lo = mid; else hi = mid - 1u;
+      }
+      lb = max(lb, lo);
+    }
+    // the kp candidates above lb certify kp elements with exact value >= lb - eps, so a candidate whose
+    // approximate value is below lb - 2 eps cannot be in the exact top-kp and is not gathered
+    const float cut = lb ? ord2f(lb) - 2.f * eps - (METRIC == LEMON_METRIC_L2 ? dbdev : 0.f) : -CUDART_INF_F;
+    // ---- 2. stage the surviving candidates (shared memory), then evaluate them exactly, four at a time
+    int ccnt = 0;
+    bool overflow = false;
+    for (int c = 0; c < nchunk; ++c) {
+      if (nchunk > 1 || c > 0) load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const bool pred = k[i] != 0ull && key_val(k[i]) >= cut && uint32_t(key_idx(k[i])) < uint32_t(m);
+        const unsigned mask = __ballot_sync(kFull, pred);
+        const int pos = ccnt + __popc(mask & ((1u << lane) - 1u));
+        if (pred && pos < kCap) cbuf[pos] = k[i];
+        ccnt += __popc(mask);
+      }
+    }
+    if (ccnt > kCap) { overflow = true; ccnt = kCap; }
+    __syncwarp();
+    const int ecnt = ccnt;
+    for (int t = 0; t < ccnt; t += 4) {
+      const float* bp[4];
+      int idx4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        idx4[j] = key_idx(cbuf[min(t + j, ccnt - 1)]);          // warp-uniform (shared memory broadcast)
+        bp[j] = db + int64_t(idx4[j]) * d;
+      }
+      float v4[4];
+      warp_pair_value4<METRIC>(qr, bp[0], bp[1], bp[2], bp[3], d, lane, v4);
+      if (lane < 4 && t + lane < ccnt) {
+        float v = lane == 0 ? v4[0] : (lane == 1 ? v4[1] : (lane == 2 ? v4[2] : v4[3]));
+        const int id = lane == 0 ? idx4[0] : (lane == 1 ? idx4[1] : (lane == 2 ? idx4[2] : idx4[3]));
+        if (METRIC == LEMON_METRIC_L2) v = -v;
+        ebuf[t + lane] = make_key(v, uint32_t(id));
+      }
     }
     __syncwarp();
+    uint64_t key[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const int e = lane * 8 + i; key[i] = e < ecnt ? ebuf[e] : 0ull; }
     warp_sort256_desc(key, lane);
-    // ---- 4. emit the exact top list
+    // ---- 3. emit the exact top list
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int e = lane * 8 + i;
@@ -97,16 +134,16 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
         top_idx[row * kp + e] = ok ? key_idx(key[i]) : -1;
       }
     }
-    // ---- 5. certificate: every column outside the lists has approximate ip <= B, hence exact ip <= B + eps
+    // ---- 4. certificate: every column outside the lists has approximate ip <= B, hence exact ip <= B + eps
     uint64_t kth_sel = 0ull;
 #pragma unroll
     for (int i = 0; i < 8; ++i) if (i == ((kp - 1) & 7)) kth_sel = key[i];
     const uint64_t kth_key = shfl_u64(kth_sel, (kp - 1) >> 3);
-    if (lane == 0 && B > -CUDART_INF_F) {
+    if (lane == 0 && (B > -CUDART_INF_F || overflow)) {
       const float dbmin = 1.f - dbdev;
       float T = B + eps;
       if (METRIC == LEMON_METRIC_L2) T = 2.f * T - qsq - dbmin;
-      const bool certified = kth_key != 0ull && key_val(kth_key) > T;
+      const bool certified = !overflow && kth_key != 0ull && key_val(kth_key) > T;
       if (!certified) {
         const int pos = atomicAdd(n_uncert, 1);
         uncert_rows[pos] = int32_t(row);

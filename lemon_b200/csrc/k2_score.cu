@@ -64,27 +64,42 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
       const float* other_db = side == 0 ? ydb : xdb;
       float rD[2], rdist[2], rdtr[2];
       int ridx[2];
-      for (int j = 0; j < k; ++j) {
-        const int idx = ti[j];
-        float dist, Dv, dtr;
-        if (idx < 0 || int64_t(idx) >= m) {
-          dist = nanv; Dv = nanv; dtr = nanv;
-        } else {
-          if (side == 0 && discrete) {
-            dist = 1.0f - float(label_db[idx] == label_q[row]);       // run_lemon.py:266-267
-          } else {
-            const float v = warp_pair_value<METRIC>(other_q, other_db + int64_t(idx) * d, d, lane);
-            dist = (METRIC == LEMON_METRIC_IP) ? 1.0f - v : v;         // :271,273,287,289
-          }
-          Dv = tv[j];
-          // cosine: D = -<a,b> (:270,286); the negation is skipped for image neighbours under the
-          // discrete text metric because it sits in the else-branch (:266-270)
-          if (METRIC == LEMON_METRIC_IP && !(side == 0 && discrete)) Dv = -Dv;
-          dtr = dists_tr[idx];
+      for (int j0 = 0; j0 < k; j0 += 4) {
+        int idx4[4];
+        const float* bp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = min(j0 + u, k - 1);
+          idx4[u] = ti[j];
+          const bool ok = idx4[u] >= 0 && int64_t(idx4[u]) < m;
+          bp[u] = other_db + int64_t(ok ? idx4[u] : 0) * d;
         }
-        if (lane == (j & 31)) {
-          if (j < 32) { rD[0] = Dv; rdist[0] = dist; rdtr[0] = dtr; ridx[0] = idx; }
-          else        { rD[1] = Dv; rdist[1] = dist; rdtr[1] = dtr; ridx[1] = idx; }
+        float v4[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!(side == 0 && discrete)) warp_pair_value4<METRIC>(other_q, bp[0], bp[1], bp[2], bp[3], d, lane, v4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          if (j >= k) break;
+          const int idx = idx4[u];
+          float dist, Dv, dtr;
+          if (idx < 0 || int64_t(idx) >= m) {
+            dist = nanv; Dv = nanv; dtr = nanv;
+          } else {
+            if (side == 0 && discrete) {
+              dist = 1.0f - float(label_db[idx] == label_q[row]);       // run_lemon.py:266-267
+            } else {
+              dist = (METRIC == LEMON_METRIC_IP) ? 1.0f - v4[u] : v4[u];  // :271,273,287,289
+            }
+            Dv = tv[j];
+            // cosine: D = -<a,b> (:270,286); the negation is skipped for image neighbours under the
+            // discrete text metric because it sits in the else-branch (:266-270)
+            if (METRIC == LEMON_METRIC_IP && !(side == 0 && discrete)) Dv = -Dv;
+            dtr = dists_tr[idx];
+          }
+          if (lane == (j & 31)) {
+            if (j < 32) { rD[0] = Dv; rdist[0] = dist; rdtr[0] = dtr; ridx[0] = idx; }
+            else        { rD[1] = Dv; rdist[1] = dist; rdtr[1] = dtr; ridx[1] = idx; }
+          }
         }
       }
       double part = 0.0;

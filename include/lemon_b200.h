@@ -160,6 +160,19 @@ int lemon_expand_groups(lemon_ctx* ctx, const float* uval, const int32_t* uidx, 
                         const int32_t* members, int64_t nq, int kp, int metric, float* top_val,
                         int32_t* top_idx, void* stream);
 
+/* Hyper-parameter grid stage (lib/metrics/utils.py:117-121,167-186,286-296): for each of n_points grid points
+ *   score_i = d1[i] + beta[g] * sn[tidx[g], i] + gamma[g] * sm[tidx[g], i]      (all float64, utils.py:77)
+ * and Brent's bounded minimiser (scipy.optimize.fminbound, xtol = xatol, maxfun) of t -> -F1(y, score >= t) on
+ * [min score, max score]; out_f1[g] = F1 at the returned threshold out_thr[g] (optimize_f1_efficient).
+ * sn/sm [n_tau, n] are the neighbour terms of each (tau_1, tau_2) combination (lemon_combine_scores / lemon_score);
+ * with sn == sm == NULL the scores are d1 itself (single call of optimize_f1_efficient).  y [n] uint8 labels.
+ * scratch: scratch_rows * n float64; one thread block per grid point, at most scratch_rows blocks resident.
+ */
+int lemon_f1_grid(lemon_ctx* ctx, const double* d1, const double* sn, const double* sm, const uint8_t* y,
+                  int64_t n, const double* beta, const double* gamma, const int32_t* tidx, int64_t n_points,
+                  double xatol, int maxfun, double* out_f1, double* out_thr, double* scratch,
+                  int64_t scratch_rows, void* stream);
+
 /* Number of kernels this library has launched through `ctx` since creation (bench "gpu_launches"). */
 int64_t lemon_launch_count(lemon_ctx* ctx);
 

@@ -11,7 +11,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblemon_b200.so")
-SOURCES = ["capi.cu", "k0_normalize.cu", "k1_knn_exact.cu", "k1_knn_tc.cu", "k2_rerank.cu", "k2_score.cu", "k3_dedup.cu"]
+SOURCES = ["capi.cu", "k0_normalize.cu", "k1_knn_exact.cu", "k1_knn_tc.cu", "k2_rerank.cu", "k2_score.cu", "k3_dedup.cu", "k4_hparam.cu"]
+EXTRA_FLAGS = {"k4_hparam.cu": ["-fmad=false"]}   # float64 operation order must follow the CPU code
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]
 
@@ -40,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *flags, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *flags, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -1,0 +1,149 @@
+"""Hyper-parameter search on the GPU: drop-ins for the reference's F1 objective
+``optimize_f1_efficient`` (lib/metrics/utils.py:286-296) and for the grid stage of ``maximize_metric``
+(utils.py:167-186), which the reference evaluates point by point on the CPU (7056 points per run,
+run_lemon.py:332-337).  All grid points are evaluated by one ``lemon_f1_grid`` launch (one thread block per
+point: scores -> Brent's bounded minimiser of -F1, the algorithm behind scipy's ``fminbound``)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from .scoring import HP_KEYS, _ptr, _stream, _to_dev, get_scorer
+
+_COLS = ("D_n", "D_m", "dists_tr_n", "dists_tr_m", "dists_n", "dists_m")
+XATOL = 1e-8          # utils.py:291 (xtol = 1e-8)
+MAXFUN = 500          # scipy.optimize.fminbound default
+
+
+def _f1_grid(sc, d1, sn, sm, y, beta, gamma, tidx):
+    dev = sc.device
+    n = d1.numel()
+    G = 1 if beta is None else beta.numel()
+    rows = int(min(G, sc.num_sms * 8))
+    out_f1 = torch.empty(G, dtype=torch.float64, device=dev)
+    out_thr = torch.empty(G, dtype=torch.float64, device=dev)
+    scratch = torch.empty((rows, n), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        sc.ctx.check(sc.lib.lemon_f1_grid(sc.ctx.handle, _ptr(d1), _ptr(sn), _ptr(sm), _ptr(y), n, _ptr(beta), _ptr(gamma),
+                                          _ptr(tidx), G, C.c_double(XATOL), MAXFUN, _ptr(out_f1), _ptr(out_thr),
+                                          _ptr(scratch), rows, _stream()), "lemon_f1_grid")
+    return out_f1, out_thr
+
+
+def optimize_f1_efficient(y, score, return_thres: bool = False):
+    """Same signature and result as lib.metrics.utils.optimize_f1_efficient (utils.py:286-296)."""
+    sc = get_scorer()
+    s = _to_dev(np.asarray(score, dtype=np.float64) if not torch.is_tensor(score) else score, sc.device, torch.float64)
+    yy = _to_dev(np.asarray(y) != 0 if not torch.is_tensor(y) else (y != 0), sc.device, torch.uint8)
+    f1, thr = _f1_grid(sc, s, None, None, yy, None, None, None)
+    f1, thr = float(f1.item()), float(thr.item())
+    return (f1, thr) if return_thres else f1
+
+
+def grid_points(grid: dict, force_zero=(), force_one=()):
+    """Vectors [beta, gamma, tau_1_n, tau_2_n, tau_1_m, tau_2_m] in the order utils.py:167-181 visits them, with
+    unpack_vector's force_zero / force_one applied (utils.py:84-103)."""
+    import itertools
+    keys = list(grid.keys())
+    pts = []
+    for values in itertools.product(*grid.values()):
+        x = dict(zip(keys, values))
+        g = []
+        for name in HP_KEYS:
+            if name in x:
+                v = x[name]
+            elif name in ("tau_1_n", "tau_1_m"):
+                v = x["tau_1"]
+            elif name in ("tau_2_n", "tau_2_m"):
+                v = x["tau_2"]
+            else:
+                raise NotImplementedError(name)
+            if name in force_zero:
+                v = 0.0
+            g.append(float(v))
+        pts.append(g)
+    eff = []
+    for g in pts:
+        e = list(g)
+        for c, name in enumerate(HP_KEYS):
+            if name in force_zero:
+                e[c] = 0.0
+        for c, name in enumerate(HP_KEYS):
+            if name in force_one:
+                e[c] = 1.0
+        eff.append(e)
+    return pts, eff
+
+
+def grid_search(rec, y, grid: dict, force_zero=(), force_one=()):
+    """Grid stage of maximize_metric (utils.py:167-186) in one launch.  rec: dict (or DataFrame) with the six
+    [N,k] record columns + d_1; y: is_mislabel.  Returns (best_x, best_f1, f1 of every point, threshold of every
+    point); ties keep the first best point, as the reference's strict `>` does."""
+    sc = get_scorer()
+    dev = sc.device
+    if hasattr(rec, "columns"):                      # legacy DataFrame
+        from .results import dataframe_to_records
+        rec = dataframe_to_records(rec)
+    pts, eff = grid_points(grid, force_zero, force_one)
+    eff_a = np.asarray(eff, dtype=np.float64)
+    taus, tidx = np.unique(eff_a[:, 2:], axis=0, return_inverse=True)
+    cols = {c: _to_dev(rec[c], dev, torch.float32) for c in _COLS}
+    d1 = _to_dev(rec["d_1"], dev, torch.float64)
+    n = d1.numel()
+    sn = torch.empty((len(taus), n), dtype=torch.float64, device=dev)
+    sm = torch.empty((len(taus), n), dtype=torch.float64, device=dev)
+    for t, tau in enumerate(taus):                   # neighbour terms once per (tau_1n, tau_2n, tau_1m, tau_2m)
+        hp = dict(zip(HP_KEYS, [0.0, 0.0, *tau]))
+        _, a, b = sc.combine_scores({**cols, "d_1": d1}, hp)
+        sn[t], sm[t] = a, b
+    yy = _to_dev(np.asarray(y) != 0, dev, torch.uint8)
+    beta = torch.from_numpy(np.ascontiguousarray(eff_a[:, 0])).to(dev)
+    gamma = torch.from_numpy(np.ascontiguousarray(eff_a[:, 1])).to(dev)
+    ti = torch.from_numpy(np.ascontiguousarray(tidx.reshape(-1).astype(np.int32))).to(dev)
+    f1, thr = _f1_grid(sc, d1, sn, sm, yy, beta, gamma, ti)
+    f1, thr = f1.cpu().numpy(), thr.cpu().numpy()
+    best = int(np.argmax(f1))                        # first maximum == strict `>` in visiting order
+    return pts[best], float(f1[best]), f1, thr
+
+
+def maximize_metric(ref_utils, df, grid, x0s, obj_func, obj_func_args, force_zero=[], force_one=[],
+                    scipy_methods=["Powell", "Nelder-Mead"]):
+    """maximize_metric (utils.py:151-196) with the grid stage on the GPU.  The scipy and LBFGS stages stay the
+    reference's own (`ref_utils.maximize_metric_scipy/_torch`, `optim_func`); with patch_reference_hparam_search
+    their objective evaluations run on the GPU as well."""
+    best_x, best_val = None, -1
+    for x in x0s:
+        for method in scipy_methods:
+            temp = ref_utils.maximize_metric_scipy(df, x, obj_func, obj_func_args, method=method,
+                                                   force_zero=force_zero, force_one=force_one)
+            if -temp.fun > best_val:
+                best_val, best_x = -temp.fun, temp.x
+    for x in x0s:
+        cand_x = ref_utils.maximize_metric_torch(df, x, obj_func, obj_func_args, force_zero=force_zero,
+                                                 force_one=force_one)["x"]
+        temp = ref_utils.optim_func(cand_x, df, obj_func, obj_func_args, force_zero=force_zero, force_one=force_one)
+        if -temp > best_val:
+            best_val, best_x = -temp, cand_x
+    gx, gval, _, _ = grid_search(df, df["is_mislabel"].values, grid, force_zero, force_one)
+    if gval > best_val:
+        best_val, best_x = gval, gx
+    best_x = list(best_x)
+    for c, name in enumerate(HP_KEYS):
+        if name in force_zero:
+            best_x[c] = 0.0
+        if name in force_one:
+            best_x[c] = 1.0
+    score = ref_utils.calc_scores_given_hparams_vectorized(
+        df, ref_utils.unpack_vector(best_x, force_zero=force_zero, force_one=force_one))
+    return best_x, best_val, obj_func(df["is_mislabel"], score, return_thres=True, **obj_func_args)[1]
+
+
+def patch_reference_hparam_search(ref_utils):
+    """lib.metrics.utils: F1 objective, scoring function and grid stage -> GPU (run_lemon.py:324-394 unchanged)."""
+    from . import metrics_compat
+    ref_utils.optimize_f1_efficient = optimize_f1_efficient
+    ref_utils.calc_scores_given_hparams_vectorized = metrics_compat.calc_scores_given_hparams_vectorized
+    ref_utils.maximize_metric = lambda *a, **k: maximize_metric(ref_utils, *a, **k)
+    return ref_utils

@@ -36,6 +36,9 @@ struct TcParams {
   uint64_t* cand_keys;  // [nq_pad][nseg][2][kCap]: the streaming key buffers ARE the output
   int32_t* cand_cnt;    // [nq_pad][nseg][2]
   float* cand_theta;    // [nq_pad][nseg][2]: every column not in the list has approximate value <= theta
+  int soft_limit;       // a row is pruned after a tile once it holds more keys than this
+  int prunes_per_tile;  // deferred prunes per tile and warp
+  int boot_tiles;       // 256-column tiles per item that only bootstrap the thresholds (8 or 16; 0 = off)
   int debug;            // LEMON_TC_DEBUG bits: 1 = epilogue does no work, 2 = filter only, 4 = exact-sort compaction
 };
 
@@ -330,21 +333,23 @@ __device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
 // column, so a value with at least 64 recorded maxima >= it is a valid threshold (at least 64 columns beat it),
 // and it is nearly as tight as the true 64th best of those tiles.  The pivot comes from a sorted sample with
 // an exact count, as in prune_one.  The bootstrap tiles are re-scanned at the end of the item.
-__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, float& theta, int lane) {
+__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, int nmax, float& theta, int lane) {
+  const bool two = nmax > 128;                       // 128 or 256 recorded maxima per row
   for (int L = 0; L < 32; ++L) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(warp_keys + size_t(L) * row_stride) + lane);
-    const float s = warp_sort32_desc_f(v.x, lane);
-    const float p0 = __shfl_sync(kFull, s, 13), p1 = __shfl_sync(kFull, s, 16), p2 = __shfl_sync(kFull, s, 20);
-    const float p3 = __shfl_sync(kFull, s, 31);
-    int c0 = (v.x >= p0) + (v.y >= p0) + (v.z >= p0) + (v.w >= p0);
-    int c1 = (v.x >= p1) + (v.y >= p1) + (v.z >= p1) + (v.w >= p1);
-    int c2 = (v.x >= p2) + (v.y >= p2) + (v.z >= p2) + (v.w >= p2);
+    const float4* src = reinterpret_cast<const float4*>(warp_keys + size_t(L) * row_stride);
+    const float4 v = __ldcg(src + lane);
+    const float4 w = two ? __ldcg(src + 32 + lane) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+    const float s = warp_sort32_desc_f(v.x, lane);   // systematic sample: every 4th (8th) maximum
+    const int r0 = two ? 6 : 13, r1 = two ? 8 : 16, r2 = two ? 11 : 20;
+    const float p0 = __shfl_sync(kFull, s, r0), p1 = __shfl_sync(kFull, s, r1), p2 = __shfl_sync(kFull, s, r2);
+    int c0 = (v.x >= p0) + (v.y >= p0) + (v.z >= p0) + (v.w >= p0) + (w.x >= p0) + (w.y >= p0) + (w.z >= p0) + (w.w >= p0);
+    int c1 = (v.x >= p1) + (v.y >= p1) + (v.z >= p1) + (v.w >= p1) + (w.x >= p1) + (w.y >= p1) + (w.z >= p1) + (w.w >= p1);
+    int c2 = (v.x >= p2) + (v.y >= p2) + (v.z >= p2) + (v.w >= p2) + (w.x >= p2) + (w.y >= p2) + (w.z >= p2) + (w.w >= p2);
     c0 = __reduce_add_sync(kFull, c0); c1 = __reduce_add_sync(kFull, c1); c2 = __reduce_add_sync(kFull, c2);
     float mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
-    (void)p3;
-    const float th = c0 >= kKeep ? p0 : (c1 >= kKeep ? p1 : (c2 >= kKeep ? p2 : mn));   // mn: all 128 maxima >= it
+    const float th = c0 >= kKeep ? p0 : (c1 >= kKeep ? p1 : (c2 >= kKeep ? p2 : mn));   // mn: 128 maxima >= it
     // the filter keeps values STRICTLY above the threshold, and the >= 64 columns that certify `th` are only
     // collected later (re-scan): step one ulp down so that columns equal to `th` (mass ties!) are kept too
     const float th_open = __uint_as_float(f2ord_dec(th));
@@ -374,7 +379,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   constexpr uint32_t kStageBytes = kBRows * kBK * 2;
   constexpr uint32_t kTmemCols = 512;              // all of TMEM: kNBuf accumulator buffers of BN columns
   constexpr uint32_t kNBuf = 512 / BN;             // 2 (BN=256) or 4 (BN=128); buffer b belongs to epilogue group b & 1
-  constexpr int kBoot = kBootTiles * 256 / BN;     // bootstrap tiles per item: 128 group maxima per epilogue group
+  const int kBoot = p.boot_tiles * 256 / BN;       // bootstrap tiles per item: 128 (or 256) group maxima per epilogue group
 
   const uint32_t a_smem = smem_base;
   const uint32_t b_smem = a_smem + uint32_t(p.kchunks) * kAChunkBytes;
@@ -537,8 +542,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
           }
-          if (bcount * (BN / 8) >= 128) {   // (single-group mode records 8 tiles but uses the first 4)            // 128 maxima recorded (4 tiles of 256 columns): set the thresholds
-            boot_select(warp_keys, row_stride, theta, lane);
+          if (bcount * (BN / 8) >= p.boot_tiles * 16) {   // all of this group's bootstrap tiles are recorded
+            boot_select(warp_keys, row_stride, p.boot_tiles * 16, theta, lane);
             __syncwarp();
             th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
             bcount = -1000000;
@@ -603,7 +608,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         // deferred, rate-limited pruning: the accumulator buffer is already released, and at most a few rows
         // are pruned per tile so that the correlated fill of the 32 rows does not turn into one long stall
-        prune_rows(warp_keys, row_stride, cnt, theta, kSoftLimit, kPrunesPerTile, lane, exact_only);
+        prune_rows(warp_keys, row_stride, cnt, theta, p.soft_limit, p.prunes_per_tile, lane, exact_only);
         th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       }
       // ---- item done: the row's key buffer already sits in the output; publish its length and threshold.
@@ -678,6 +683,11 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   p.cand_keys = cand_keys; p.cand_cnt = cand_cnt; p.cand_theta = cand_theta;
   const char* dbg = getenv("LEMON_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
+  const char* e1 = getenv("LEMON_TC_SOFT");   p.soft_limit = e1 ? atoi(e1) : kSoftLimit;
+  const char* e2 = getenv("LEMON_TC_PPT");    p.prunes_per_tile = e2 ? atoi(e2) : kPrunesPerTile;
+  const char* e3 = getenv("LEMON_TC_BOOT");   p.boot_tiles = e3 ? atoi(e3) : kBootTiles;
+  if (p.boot_tiles != 0 && p.boot_tiles != 8 && p.boot_tiles != 16) p.boot_tiles = kBootTiles;
+  if (p.soft_limit < 64 || p.soft_limit > kCap - 32) p.soft_limit = kSoftLimit;
 
   int64_t units = ctx->num_sms / CG;
   if (units > p.n_items) units = p.n_items;

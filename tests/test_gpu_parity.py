@@ -380,3 +380,25 @@ def test_duplicate_rows_are_searched_once_and_expanded_exactly(lb):
     assert dd.db["y"].dedup is not None and dd.db["y"].dedup.n_unique < 4600
     for c in a:
         assert (a[c] == b[c]).all(), c
+
+
+def test_faiss_compat_unnormalised_vectors_on_the_tensor_core_path(lb):
+    """faiss semantics do not normalise: vectors of assorted norms, DB large enough for K1.  The certificate uses
+    the rows' actual norms; whatever it cannot certify (all of L2 here: the norms are far from 1) goes through the
+    exact GPU fallback — results must equal the oracle either way."""
+    from lemon_b200 import faiss_compat as faiss
+    from oracle import lemon_oracle as O
+    rng = np.random.RandomState(5)
+    x, _, _, _ = clustered_pairs(6000, 96, n_clusters=40, seed=33)
+    x = (x * rng.uniform(0.3, 2.5, (6000, 1))).astype(np.float32)
+    q = (x[:400] + 0.02 * rng.standard_normal((400, 96))).astype(np.float32)
+    for cls, metric in ((faiss.IndexFlatIP, "ip"), (faiss.IndexFlatL2, "l2")):
+        index = cls(96)
+        index.add(x)
+        D, I = index.search(q, 12)
+        Dr, Ir = O.knn_search(q, x, 12, metric)
+        r = O.compare_neighbor_sets(q, x, I, 12, metric, eps_tie=2e-5, D_ref=Dr, I_ref=Ir)
+        assert r["wrong"] == 0, (metric, r["wrong_rows"][:5])
+        same = (I == Ir).all(1)
+        assert same.mean() > 0.98
+        np.testing.assert_allclose(D[same], Dr[same], rtol=2e-5, atol=1e-5)

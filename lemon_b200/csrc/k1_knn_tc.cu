@@ -1,18 +1,20 @@
 // K1: tensor-core candidate search.  Replaces faiss IndexFlatIP.search (run_lemon.py:235-236)
 // for the bulk of the work: S = Q * DB^T on tcgen05 (fp16 operands, fp32 TMEM accumulators) with a
-// streaming top-64 fused into the epilogue, so the nq x m similarity matrix never reaches HBM.
+// streaming top-k fused into the epilogue, so the nq x m similarity matrix never reaches HBM.
 //
-// Structure (one persistent CTA, or CTA pair with cta_group::2, per SM):
-//   warp 0   TMA producer : query tile (resident in SMEM for the whole DB scan) + DB tiles (ring)
-//   warp 1   MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
-//                            double-buffered in TMEM (2 x BN columns)
-//   warp 2   TMEM alloc / dealloc
-//   warps 4-11 epilogue   : tcgen05.ld 32x32b (thread == query row), threshold filter in registers,
-//                            8-column groups holding a survivor are staged raw in L2-resident global
-//                            scratch; the warp then filters a row's staged groups cooperatively into the
-//                            row's 256-entry key buffer and prunes it to ~64-160 keys when it fills.
+// Structure (one persistent CTA pair with cta_group::2 -- or single CTA -- per SM, 384 threads):
+//   warp 0    TMA producer : query tile (resident in SMEM for the whole DB scan) + DB tiles (ring)
+//   warp 1    MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
+//                             double-buffered in TMEM (512 columns)
+//   warp 2    TMEM alloc / dealloc
+//   warps 4-11 epilogue    : two groups of four warps, group g owns TMEM buffer g.  tcgen05.ld 32x32b
+//                             (thread == query row), FMNMX3 max tree against the row's threshold, survivors
+//                             appended as 64-bit keys to the row's 256-slot list (which lives in the OUTPUT
+//                             array), sample-pivot pruning deferred until the TMEM buffer is handed back,
+//                             thresholds shared between the groups, threshold bootstrap from group maxima.
 // Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
-// in the same order and DB tiles are served from L2.
+// in the same order and DB tiles are served from L2.  The union / top-64 selection over a row's lists
+// is done by the re-rank kernel (k2_rerank.cu).
 #include <cuda.h>
 #include <cstdlib>
 

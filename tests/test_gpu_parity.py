@@ -402,3 +402,36 @@ def test_faiss_compat_unnormalised_vectors_on_the_tensor_core_path(lb):
         same = (I == Ir).all(1)
         assert same.mean() > 0.98
         np.testing.assert_allclose(D[same], Dr[same], rtol=2e-5, atol=1e-5)
+
+
+def test_tail_launch_and_segments_equal_exact_path(lb):
+    """Row count just above one full round of CTA pairs: the scorer sends the last rows to a second,
+    DB-segmented launch (plan_tail); results must equal the brute-force kernel bit for bit."""
+    from lemon_b200 import plan_tail
+    sc = lb.get_scorer()
+    units = sc.num_sms // 2
+    nq, m, d = units * 256 + 700, 20000, 64
+    n_main, nseg = plan_tail(nq, m, sc.num_sms, 2)
+    assert n_main == units * 256 and nseg >= 2
+    x, _, _, _ = clustered_pairs(m, d, n_clusters=80, seed=123)
+    q = np.concatenate([x, x[: nq - m] * 0.5 + x[7:7 + nq - m] * 0.5]) if nq > m else x[:nq]
+    qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
+    tv, ti = sc.knn(qp, dbp, 31, 0, mode="tc")
+    assert isinstance(sc.last_info["nseg"], list) and sc.last_info["nseg"][1] == nseg
+    ev, ei = sc.knn(qp, dbp, 31, 0, mode="exact")
+    assert bool((ti == ei).all()) and bool((tv == ev).all())
+
+
+def test_sharded_driver_host_inputs_equal_device_inputs(lb):
+    """Pinned host shards (copy stream, image side overlapped with the text copy) == device shards, bitwise."""
+    import torch
+    from lemon_b200 import dist as ldist
+    x, y, _, _ = clustered_pairs(5000, 512, n_clusters=40, seed=77, noise_frac=0.3)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    a = ldist.score_pairs_sharded(xd, yd, 5000, k=12, hparams=HP)
+    b = ldist.score_pairs_sharded(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), 5000, k=12, hparams=HP)
+    torch.cuda.synchronize()
+    assert a["rows"] == b["rows"] == (0, 5000)
+    for c in ("score", "I_n", "I_m", "D_n", "dists_m", "d_1"):
+        assert bool((a[c] == b[c]).all()), c
+    check_against_oracle(_np({k: v for k, v in b.items() if k != "rows"}), x, y, x, y, k=12, query_in_db=np.arange(5000), hparams=HP)

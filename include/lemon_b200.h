@@ -173,6 +173,17 @@ int lemon_f1_grid(lemon_ctx* ctx, const double* d1, const double* sn, const doub
                   double xatol, int maxfun, double* out_f1, double* out_thr, double* scratch,
                   int64_t scratch_rows, void* stream);
 
+/* Discrepancy / diversity baseline scores (lib/baselines/discrepancy_baseline.py:213-230) from kNN lists.
+ *   emb [m,d]: the modality matrix the score reads (text for *_y, image for *_x); qemb [nq,d]: the query's embedding
+ *   in that modality (mode 0 only); nn [nq,kk]: text-kNN list of every query (kk = k, or k+1 for train queries);
+ *   cache [m,kc]: text-kNN list of every DB row, kc = k+1, the row itself is skipped (mode 0 only).
+ *   mode 0 (dis_x / dis_y): out = sum(1 - <emb[l], qemb>) / L over the second-order neighbours l;
+ *   mode 1 (div_x / div_y): out = sum_ab (1 - <emb[a], emb[b]>) / k^2 over the first-order neighbours.
+ */
+int lemon_discrepancy(lemon_ctx* ctx, const float* emb, const float* qemb, const int32_t* nn,
+                      const int32_t* cache, int64_t nq, int64_t m, int d, int kk, int kc, int k, int mode,
+                      float* out, void* stream);
+
 /* Number of kernels this library has launched through `ctx` since creation (bench "gpu_launches"). */
 int64_t lemon_launch_count(lemon_ctx* ctx);
 

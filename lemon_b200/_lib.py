@@ -44,6 +44,8 @@ SIGNATURES = {
                                       c_i32p, C.c_void_p]),
     "lemon_f1_grid": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, C.c_void_p, C.c_int64, c_f64p, c_f64p, c_i32p,
                                 C.c_int64, C.c_double, C.c_int, c_f64p, c_f64p, c_f64p, C.c_int64, C.c_void_p]),
+    "lemon_discrepancy": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, c_f32p, C.c_void_p]),
     "lemon_combine_scores": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f64p, C.c_int64,
                                        C.c_int, C.POINTER(C.c_double), c_f64p, c_f64p, c_f64p, C.c_void_p]),
 }

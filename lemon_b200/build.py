@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblemon_b200.so")
-SOURCES = ["capi.cu", "k0_normalize.cu", "k1_knn_exact.cu", "k1_knn_tc.cu", "k2_rerank.cu", "k2_score.cu", "k3_dedup.cu", "k4_hparam.cu"]
+SOURCES = ["capi.cu", "k0_normalize.cu", "k1_knn_exact.cu", "k1_knn_tc.cu", "k2_rerank.cu", "k2_score.cu", "k3_dedup.cu", "k4_hparam.cu", "k5_discrepancy.cu"]
 EXTRA_FLAGS = {"k4_hparam.cu": ["-fmad=false"]}   # float64 operation order must follow the CPU code
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--use_fast_math=false"]

@@ -435,3 +435,32 @@ def test_sharded_driver_host_inputs_equal_device_inputs(lb):
     for c in ("score", "I_n", "I_m", "D_n", "dists_m", "d_1"):
         assert bool((a[c] == b[c]).all()), c
     check_against_oracle(_np({k: v for k, v in b.items() if k != "rows"}), x, y, x, y, k=12, query_in_db=np.arange(5000), hparams=HP)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_fuzz_shapes_default_path_equals_exact_and_oracle(lb, seed):
+    """Random shapes through knn(): tiny and mid-size DBs (exact kernel), TC-sized DBs, odd dims, k up to 63, both
+    metrics.  The default path must equal the brute-force kernel bit for bit, and the oracle modulo eps-ties."""
+    from oracle import lemon_oracle as O
+    rng = np.random.RandomState(1000 + seed)
+    m = int(rng.choice([40, 300, 1900, 2500, 7000, 17000]))
+    nq = int(rng.choice([1, 33, 200, 600]))
+    d = int(rng.choice([20, 100, 300, 512, 640, 768]))
+    kp = int(rng.choice([1, 2, 6, 31, 51, 63]))
+    metric = int(rng.randint(0, 2))
+    x, _, _, _ = clustered_pairs(m, d, n_clusters=max(2, m // 50), seed=seed)
+    q = (x[rng.randint(0, m, nq)] + 0.05 * rng.standard_normal((nq, d))).astype(np.float32)
+    sc = lb.get_scorer()
+    qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
+    tv, ti = sc.knn(qp, dbp, kp, metric)                      # default ("auto") path
+    ev, ei = sc.knn(qp, dbp, kp, metric, mode="exact")
+    assert bool((ti == ei).all()) and bool((tv == ev).all()), (m, nq, d, kp, metric)
+    qn, xn = qp.f32.cpu().numpy()[:, :d], dbp.f32.cpu().numpy()[:, :d]
+    name = "ip" if metric == 0 else "l2"
+    D, I = O.knn_search(qn, xn, kp, name)
+    got = ti.cpu().numpy().astype(np.int64)
+    if m >= kp:
+        r = O.compare_neighbor_sets(qn, xn, got, kp, name, eps_tie=4e-6, D_ref=D, I_ref=I)
+        assert r["wrong"] == 0, (m, nq, d, kp, metric, r["wrong_rows"][:3])
+    else:
+        assert (got[:, m:] == -1).all() and (np.sort(got[:, :m], 1) == np.arange(m)).all()

@@ -80,6 +80,7 @@ int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* ou
  *   nq_pad = nq rounded up to a multiple of 256 rows; the caller allocates all three arrays for nq_pad rows:
  *     cand_keys  [nq_pad, nseg*2, 256] uint64: key = (order-preserving bits of the approximate inner product) << 32
  *                | ~db_row; only the first cand_cnt entries of a list are valid, in no particular order;
+ *                the array must be 2048-byte aligned (one list = 2 KB; LEMON_ERR_INVALID otherwise);
  *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. 256);
  *     cand_theta [nq_pad, nseg*2] fp32: every DB column of that list's share of the scan that is NOT in the list
  *                has approximate inner product <= theta (-inf: the list holds everything it saw).

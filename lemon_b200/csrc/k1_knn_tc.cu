@@ -171,6 +171,26 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
       :
       : "memory");
 }
+// Branch-free survivor append: `if (v > theta) { *p++ = make_key(v, ~nidx); }` as six straight-line instructions
+// (compare, two for the order-preserving bit pattern, one for the index word, predicated 64-bit store, predicated
+// pointer bump).  The compiler's version of the same statement is a divergent branch around a 13-instruction body
+// per element (BSSY / BRA / BSYNC), whose latency -- not its instruction count -- bounded the epilogue.
+// The write pointer is kept as (plo, phi): a row's key list is 2 KB and 2 KB-aligned (checked on the host), so the
+// low word never carries.
+__device__ __forceinline__ void append_if_above(uint32_t& plo, uint32_t phi, float v, float theta, uint32_t nidx) {
+  asm volatile(
+      "{\n .reg .pred p;\n .reg .b32 t, hi;\n .reg .b64 a;\n"
+      " setp.gt.f32 p, %1, %2;\n"
+      " shr.s32 t, %3, 31;\n"
+      " or.b32 t, t, 0x80000000;\n"
+      " xor.b32 hi, t, %3;\n"
+      " mov.b64 a, {%0, %4};\n"
+      " @p st.global.v2.b32 [a], {%5, hi};\n"
+      " @p add.u32 %0, %0, 8;\n}"
+      : "+r"(plo)
+      : "f"(v), "f"(theta), "r"(__float_as_uint(v)), "r"(phi), "r"(nidx)
+      : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
@@ -509,6 +529,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kCap) +
                             size_t(grp) * kCap;
       uint64_t* my_keys = warp_keys + size_t(lane) * row_stride;
+      const uint32_t keys_lo = uint32_t(reinterpret_cast<uintptr_t>(my_keys)), keys_hi = uint32_t(reinterpret_cast<uintptr_t>(my_keys) >> 32);
       th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       const int nboot = ntiles >= kBootMinTiles ? kBoot : 0;
       const int64_t nsteps = ntiles + nboot;
@@ -585,16 +606,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
             // warp-uniform gating (votes), so that groups without a survivor in ANY lane are really skipped
             if (__any_sync(kFull, mx > theta)) {
-              const uint32_t idx0 = uint32_t(colb + c);
+              const uint32_t nidx0 = ~uint32_t(colb + c);   // ~(idx0 + j) == ~idx0 - j
+              uint32_t plo = keys_lo + uint32_t(cnt) * 8u;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (__any_sync(kFull, gm[g] > theta)) {
 #pragma unroll
-                  for (int j = 8 * g; j < 8 * g + 8; ++j) {
-                    if (v[j] > theta) { my_keys[cnt] = make_key(v[j], idx0 + j); ++cnt; }
-                  }
+                  for (int j = 8 * g; j < 8 * g + 8; ++j) append_if_above(plo, keys_hi, v[j], theta, nidx0 - uint32_t(j));
                 }
               }
+              cnt = int((plo - keys_lo) >> 3);
             }
             __syncwarp();
             if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, row_stride, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow
@@ -724,8 +745,9 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
-      nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15))
-    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands)", LEMON_MAX_D_TC);
+      nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
+      (uintptr_t(cand_keys) & (kCap * 8 - 1)))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 2 KB-aligned cand_keys)", LEMON_MAX_D_TC);
   if (nq == 0) return LEMON_OK;
   if (cta_group == 0) cta_group = 2;   // CTA pairs: half the SMEM/L2 operand traffic per MMA
   cudaStream_t st = (cudaStream_t)stream;

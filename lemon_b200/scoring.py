@@ -250,7 +250,10 @@ class LemonScorer:
             nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2, db.d16)
         nlist = 2 * nseg
         nq_pad = -(-q.n // 256) * 256
-        cand_keys = torch.empty((nq_pad, nlist, LIST_CAP), dtype=torch.int64, device=self.device)
+        # K1 addresses a row's 2 KB key list with a 32-bit pointer bump: the array must be 2 KB-aligned
+        raw = torch.empty(nq_pad * nlist * LIST_CAP + LIST_CAP, dtype=torch.int64, device=self.device)
+        skip = (-raw.data_ptr() % (LIST_CAP * 8)) // 8
+        cand_keys = raw[skip: skip + nq_pad * nlist * LIST_CAP].view(nq_pad, nlist, LIST_CAP)
         cand_cnt = torch.empty((nq_pad, nlist), dtype=torch.int32, device=self.device)
         cand_theta = torch.empty((nq_pad, nlist), dtype=torch.float32, device=self.device)
         ev = None

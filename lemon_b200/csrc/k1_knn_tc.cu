@@ -7,11 +7,13 @@
 //   warp 1    MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
 //                             double-buffered in TMEM (512 columns)
 //   warp 2    TMEM alloc / dealloc
-//   warps 4-11 epilogue    : two groups of four warps, group g owns TMEM buffer g.  tcgen05.ld 32x32b
-//                             (thread == query row), FMNMX3 max tree against the row's threshold, survivors
-//                             appended as 64-bit keys to the row's 256-slot list (which lives in the OUTPUT
-//                             array), sample-pivot pruning deferred until the TMEM buffer is handed back,
-//                             thresholds shared between the groups, threshold bootstrap from group maxima.
+//   warps 4-11 epilogue    : two groups of four warps; group g scans column half g of EVERY accumulator tile
+//                             (so a buffer is held for half a scan time and no group idles while "its" buffer
+//                             is being refilled).  tcgen05.ld 32x32b (thread == query row), FMNMX3 max tree
+//                             against the row's threshold, survivors appended branch-free as 64-bit keys to the
+//                             row's 256-slot list (which lives in the OUTPUT array), sample-pivot pruning
+//                             deferred until the TMEM buffer is handed back, thresholds shared between the
+//                             groups, threshold bootstrap from group maxima.
 // Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
 // in the same order and DB tiles are served from L2.  The union / top-64 selection over a row's lists
 // is done by the re-rank kernel (k2_rerank.cu).
@@ -175,20 +177,21 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
 // (compare, two for the order-preserving bit pattern, one for the index word, predicated 64-bit store, predicated
 // pointer bump).  The compiler's version of the same statement is a divergent branch around a 13-instruction body
 // per element (BSSY / BRA / BSYNC), whose latency -- not its instruction count -- bounded the epilogue.
-// The write pointer is kept as (plo, phi): a row's key list is 2 KB and 2 KB-aligned (checked on the host), so the
-// low word never carries.
-__device__ __forceinline__ void append_if_above(uint32_t& plo, uint32_t phi, float v, float theta, uint32_t nidx) {
+// Only the low word of the write pointer is bumped: a row's key list is 2 KB and 2 KB-aligned (checked on the
+// host), so it never carries.
+__device__ __forceinline__ void append_if_above(uint64_t& ptr, float v, float theta, uint32_t nidx) {
   asm volatile(
-      "{\n .reg .pred p;\n .reg .b32 t, hi;\n .reg .b64 a;\n"
+      "{\n .reg .pred p;\n .reg .b32 t, hi, lo, ph;\n"
       " setp.gt.f32 p, %1, %2;\n"
       " shr.s32 t, %3, 31;\n"
       " or.b32 t, t, 0x80000000;\n"
       " xor.b32 hi, t, %3;\n"
-      " mov.b64 a, {%0, %4};\n"
-      " @p st.global.v2.b32 [a], {%5, hi};\n"
-      " @p add.u32 %0, %0, 8;\n}"
-      : "+r"(plo)
-      : "f"(v), "f"(theta), "r"(__float_as_uint(v)), "r"(phi), "r"(nidx)
+      " @p st.global.v2.b32 [%0], {%4, hi};\n"
+      " mov.b64 {lo, ph}, %0;\n"
+      " @p add.u32 lo, lo, 8;\n"
+      " mov.b64 %0, {lo, ph};\n}"
+      : "+l"(ptr)
+      : "f"(v), "f"(theta), "r"(__float_as_uint(v)), "r"(nidx)
       : "memory");
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
@@ -223,7 +226,7 @@ constexpr int kSoftLimit = 176;                // a row is pruned after a tile o
 constexpr int kPrunesPerTile = 3;
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
 constexpr int kBootMinTiles = 64;              // items shorter than this run without the bootstrap
-constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g owns TMEM accumulator buffer g
+constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g scans column half g of every accumulator tile
 
 // Prunes one row's key buffer `b` (cntL valid keys; all lanes pass the same arguments).  Fast path: a
 // pivot is picked from a sorted systematic sample of the buffer (every 8th slot) such that at least 64
@@ -393,14 +396,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();   // SWIZZLE_128B tiles need 1024 B alignment
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the shuffle tells ptxas that the warp index is warp-uniform (uniform registers / branches in the role code)
+  const int warp = __shfl_sync(0xffffffffu, int(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0;
   const int64_t unit = blockIdx.x / CG;            // CTA (pair) id
   const int64_t n_units = gridDim.x / CG;
   constexpr int kBRows = BN / CG;                  // DB rows this CTA stages per tile
   constexpr uint32_t kStageBytes = kBRows * kBK * 2;
   constexpr uint32_t kTmemCols = 512;              // all of TMEM: kNBuf accumulator buffers of BN columns
-  constexpr uint32_t kNBuf = 512 / BN;             // 2 (BN=256) or 4 (BN=128); buffer b belongs to epilogue group b & 1
+  constexpr uint32_t kNBuf = 512 / BN;             // 2 (BN=256) or 4 (BN=128)
+  constexpr int kGrpCols = BN / kEpiGroups;        // accumulator columns each epilogue group scans per tile
   const int kBoot = p.boot_tiles * 256 / BN;       // bootstrap tiles per item: 128 (or 256) group maxima per epilogue group
 
   const uint32_t a_smem = smem_base;
@@ -421,7 +426,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     for (int s = 0; s < p.nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int b = 0; b < int(kNBuf); ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4); }
+    for (int b = 0; b < int(kNBuf); ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4 * kEpiGroups); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, kTmemCols);
@@ -501,11 +506,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     }
   } else if (warp >= 4) {
     // =============================== epilogue: streaming top-64 ===============================
-    // Two groups of 4 warps; group g consumes the tiles that land in TMEM accumulator buffer g, so each
-    // group has two MMA tile-times per tile.  Both groups track the same query rows; each keeps its own
-    // key buffer and they exchange thresholds through shared memory (a threshold certified by either
-    // group is a valid filter for both).  At the end of an item group 1 hands its best 64 per row to
-    // group 0, which merges and writes the candidates.
+    // Two groups of 4 warps; group g scans columns [g*BN/2, (g+1)*BN/2) of every accumulator tile.  (Groups that
+    // alternate whole tiles cannot scan while their buffer is being refilled: the step time was T_mma + T_scan
+    // per two tiles; with split tiles it is max(T_mma, T_scan/2 + pruning) per tile.)  Both groups track the
+    // same query rows; each keeps its own key buffer and they exchange thresholds through shared memory (a
+    // threshold certified by either group is a valid filter for both).
     const int grp = (warp - 4) >> 2;
     const bool one_group = false;
     if (!(one_group && grp == 1)) {
@@ -529,7 +534,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kCap) +
                             size_t(grp) * kCap;
       uint64_t* my_keys = warp_keys + size_t(lane) * row_stride;
-      const uint32_t keys_lo = uint32_t(reinterpret_cast<uintptr_t>(my_keys)), keys_hi = uint32_t(reinterpret_cast<uintptr_t>(my_keys) >> 32);
+      const uint32_t keys_lo = uint32_t(reinterpret_cast<uintptr_t>(my_keys));
       th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       const int nboot = ntiles >= kBootMinTiles ? kBoot : 0;
       const int64_t nsteps = ntiles + nboot;
@@ -537,15 +542,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       for (int64_t i = 0; i < nsteps; ++i, ++tc) {
         const int64_t t = i < ntiles ? i : i - ntiles;
         const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
-        if (!one_group && int(buf & 1) != grp) continue;
         mbar_wait(tmem_full + 8 * buf, use & 1);
         tc_fence_after();
         if (i < nboot && bcount >= 0) {
           // ---- bootstrap tile: record the 8-column group maxima only (no appends, no prunes)
-          const uint32_t taddr_b = tmem_base + tmem_lane + buf * BN;
-          float4* bf = reinterpret_cast<float4*>(my_keys) + bcount * (BN / 32);
+          const uint32_t taddr_b = tmem_base + tmem_lane + buf * BN + grp * kGrpCols;
+          float4* bf = reinterpret_cast<float4*>(my_keys) + bcount * (kGrpCols / 32);
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = 0; ch < kGrpCols / 32; ++ch) {
             uint32_t r[32];
             tmem_ld32_async(taddr_b + ch * 32, r);
             tmem_wait_ld(r);
@@ -565,7 +569,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
           }
-          if (bcount * (BN / 8) >= p.boot_tiles * 16) {   // all of this group's bootstrap tiles are recorded
+          if (bcount * (kGrpCols / 8) >= p.boot_tiles * 16) {   // all of this group's bootstrap tiles are recorded
             boot_select(warp_keys, row_stride, p.boot_tiles * 16, theta, lane);
             __syncwarp();
             th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
@@ -577,12 +581,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           const uint64_t o = th_sh[(grp ^ 1) * kBM + row_local];
           if (!one_group && (o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
         }
-        const int64_t colb = col0 + t * BN;
-        const int valid = int(min(int64_t(BN), col1 - colb));
-        const uint32_t taddr = tmem_base + tmem_lane + buf * BN;
+        const int64_t colb = col0 + t * BN + grp * kGrpCols;          // this group's half of the tile
+        const int valid = int(max(int64_t(0), min(int64_t(kGrpCols), col1 - colb)));
+        const uint32_t taddr = tmem_base + tmem_lane + buf * BN + grp * kGrpCols;
         if (!(p.debug & 1)) {
           const int nchunks = (valid + 31) >> 5;
-          const bool partial = valid < BN;     // only the last tile of a segment
+          const bool partial = valid < kGrpCols;     // only the last tile of a segment
 #pragma unroll 1
           for (int ch = 0; ch < nchunks; ++ch) {
             const int c = ch * 32;
@@ -607,15 +611,15 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             // warp-uniform gating (votes), so that groups without a survivor in ANY lane are really skipped
             if (__any_sync(kFull, mx > theta)) {
               const uint32_t nidx0 = ~uint32_t(colb + c);   // ~(idx0 + j) == ~idx0 - j
-              uint32_t plo = keys_lo + uint32_t(cnt) * 8u;
+              uint64_t wp = reinterpret_cast<uint64_t>(my_keys + cnt);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (__any_sync(kFull, gm[g] > theta)) {
 #pragma unroll
-                  for (int j = 8 * g; j < 8 * g + 8; ++j) append_if_above(plo, keys_hi, v[j], theta, nidx0 - uint32_t(j));
+                  for (int j = 8 * g; j < 8 * g + 8; ++j) append_if_above(wp, v[j], theta, nidx0 - uint32_t(j));
                 }
               }
-              cnt = int((plo - keys_lo) >> 3);
+              cnt = int((uint32_t(wp) - keys_lo) >> 3);
             }
             __syncwarp();
             if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, row_stride, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow

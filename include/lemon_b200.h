@@ -47,7 +47,7 @@ enum lemon_status {
 enum lemon_metric { LEMON_METRIC_IP = 0, LEMON_METRIC_L2 = 1 };
 
 #define LEMON_KPRIME 64          /* a row's candidate lists together hold its 64 best approximate values */
-#define LEMON_LIST_CAP 256       /* slots per candidate list */
+#define LEMON_LIST_CAP 1024      /* slots per candidate list */
 #define LEMON_MAX_KP 64          /* largest k (+1 for self-exclusion) a top list can hold */
 #define LEMON_MAX_D_TC 768       /* largest padded dim the tensor-core kernel keeps resident */
 
@@ -78,17 +78,20 @@ int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* ou
  *   nseg  number of DB segments scanned independently (load balance for small nq); >= 1
  *   Output = LEMON_NLIST(nseg) = nseg * 2 candidate lists per query row (two epilogue warp groups per segment).
  *   nq_pad = nq rounded up to a multiple of 256 rows; the caller allocates all three arrays for nq_pad rows:
- *     cand_keys  [nq_pad, nseg*2, 256] uint64: key = (order-preserving bits of the approximate inner product) << 32
+ *     cand_keys  [nq_pad, nseg*2, LEMON_LIST_CAP] uint64: key = (order-preserving bits of the approximate inner product) << 32
  *                | ~db_row; only the first cand_cnt entries of a list are valid, in no particular order;
- *                the array must be 2048-byte aligned (one list = 2 KB; LEMON_ERR_INVALID otherwise);
- *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. 256);
+ *                the array must be 8192-byte aligned (one list = 8 KB; LEMON_ERR_INVALID otherwise);
+ *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. LEMON_LIST_CAP);
  *     cand_theta [nq_pad, nseg*2] fp32: every DB column of that list's share of the scan that is NOT in the list
  *                has approximate inner product <= theta (-inf: the list holds everything it saw).
- *   Together the lists of a row contain its 64 best approximate inner products (ties: lower DB rows first).
+ *   keep (8 .. LEMON_KPRIME; 0 = LEMON_KPRIME): every list whose scan share is long enough holds at least `keep`
+ *   columns above its cand_theta, so together the lists of a row contain its `keep` best approximate inner products
+ *   (ties: lower DB rows first).  A smaller `keep` means fewer appended keys; callers that need the top kp choose
+ *   keep > kp with a margin for the fp16 rounding error (lemon_rerank certifies the result either way).
  *   cta_group: 1 or 2 (2 = cta_group::2 CTA pairs, 256 query rows per pair); 0 = library default.
  */
 int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
-                         int d16, int nseg, int cta_group, uint64_t* cand_keys, int32_t* cand_cnt,
+                         int d16, int nseg, int cta_group, int keep, uint64_t* cand_keys, int32_t* cand_cnt,
                          float* cand_theta, void* stream);
 
 /* fp32 exact re-rank of the candidates + per-row certificate (K2a).

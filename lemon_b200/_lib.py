@@ -28,7 +28,7 @@ SIGNATURES = {
                                        C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "lemon_rowwise_dist": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "lemon_knn_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
-                                       C.c_int, c_i64p, c_i32p, c_f32p, C.c_void_p]),
+                                       C.c_int, C.c_int, c_i64p, c_i32p, c_f32p, C.c_void_p]),
     "lemon_rerank": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_float,
                                C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_i32p, c_i32p,
                                c_i32p, C.c_void_p]),

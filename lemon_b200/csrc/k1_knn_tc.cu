@@ -40,10 +40,9 @@ struct TcParams {
   uint64_t* cand_keys;  // [nq_pad][nseg][2][kCap]: the streaming key buffers ARE the output
   int32_t* cand_cnt;    // [nq_pad][nseg][2]
   float* cand_theta;    // [nq_pad][nseg][2]: every column not in the list has approximate value <= theta
-  int soft_limit;       // a row is pruned after a tile once it holds more keys than this
-  int prunes_per_tile;  // deferred prunes per tile and warp
+  int cert;             // ladder: exceedance count that certifies a level (`keep` of the C ABI)
   int boot_tiles;       // 256-column tiles per item that only bootstrap the thresholds (8 or 16; 0 = off)
-  int debug;            // LEMON_TC_DEBUG bits: 1 = epilogue does no work, 2 = filter only, 4 = exact-sort compaction
+  int debug;            // LEMON_TC_DEBUG bits: 1 = epilogue does no work, 2 = filter only
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -177,7 +176,7 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
 // (compare, two for the order-preserving bit pattern, one for the index word, predicated 64-bit store, predicated
 // pointer bump).  The compiler's version of the same statement is a divergent branch around a 13-instruction body
 // per element (BSSY / BRA / BSYNC), whose latency -- not its instruction count -- bounded the epilogue.
-// Only the low word of the write pointer is bumped: a row's key list is 2 KB and 2 KB-aligned (checked on the
+// Only the low word of the write pointer is bumped: a row's key list is 8 KB and 8 KB-aligned (checked on the
 // host), so it never carries.
 __device__ __forceinline__ void append_if_above(uint64_t& ptr, float v, float theta, uint32_t nidx) {
   asm volatile(
@@ -222,88 +221,9 @@ __device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
   return key;
 }
 
-constexpr int kSoftLimit = 176;                // a row is pruned after a tile once it holds more keys than this
-constexpr int kPrunesPerTile = 3;
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
 constexpr int kBootMinTiles = 64;              // items shorter than this run without the bootstrap
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g scans column half g of every accumulator tile
-
-// Prunes one row's key buffer `b` (cntL valid keys; all lanes pass the same arguments).  Fast path: a
-// pivot is picked from a sorted systematic sample of the buffer (every 8th slot) such that at least 64
-// keys are >= pivot (counted exactly on the full 64-bit keys, so ties are not an issue); those keys are
-// kept and the row's threshold rises to the pivot's value.  When no sampled pivot qualifies the warp
-// falls back to the exact bitonic sort and keeps exactly the best 64.
-__device__ __forceinline__ void load_keys_raw(const uint64_t* b, ulonglong2 (&raw)[4], int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) raw[i] = __ldcg(reinterpret_cast<const ulonglong2*>(b + lane * 8 + 2 * i));
-}
-__device__ __forceinline__ void prune_one(uint64_t* b, const ulonglong2 (&raw)[4], int& cntL, float& thL, int lane,
-                                          bool exact_only) {
-  uint64_t key[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    key[2 * i] = (lane * 8 + 2 * i) < cntL ? raw[i].x : 0ull;
-    key[2 * i + 1] = (lane * 8 + 2 * i + 1) < cntL ? raw[i].y : 0ull;
-  }
-  if (!exact_only) {
-    const uint64_t s = warp_sort32_desc(key[0], lane);
-    const uint64_t p0 = shfl_u64(s, 8), p1 = shfl_u64(s, 11), p2 = shfl_u64(s, 15);
-    int c0 = 0, c1 = 0, c2 = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { c0 += key[i] >= p0; c1 += key[i] >= p1; c2 += key[i] >= p2; }
-    c0 = __reduce_add_sync(kFull, c0); c1 = __reduce_add_sync(kFull, c1); c2 = __reduce_add_sync(kFull, c2);
-    uint64_t pv = 0ull; int keep = 0;
-    if (c0 >= kKeep) { pv = p0; keep = c0; } else if (c1 >= kKeep) { pv = p1; keep = c1; } else if (c2 >= kKeep) { pv = p2; keep = c2; }
-    if (pv != 0ull && keep <= 160) {
-      int mine = 0;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mine += key[i] >= pv;
-      int incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-      int pos = incl - mine;
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) if (key[i] >= pv) { b[pos] = key[i]; ++pos; }
-      __syncwarp();
-      thL = key_val(pv); cntL = keep;
-      return;
-    }
-  }
-  warp_sort256_desc(key, lane);
-  __syncwarp();
-  if (lane < kKeep / 8) {
-#pragma unroll
-    for (int i = 0; i < 8; i += 2)
-      *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key[i], key[i + 1]);
-  }
-  const uint64_t k64 = shfl_u64(key[7], kKeep / 8 - 1);
-  if (cntL >= kKeep) { thL = key_val(k64); cntL = kKeep; }
-  __syncwarp();
-}
-
-// Prunes the buffers of (at most max_rows of) the lanes whose key count passed `limit`.  The next row's
-// keys are fetched from L2 while the current row is processed.
-__device__ __forceinline__ void prune_rows(uint64_t* warp_keys, size_t row_stride, int& cnt, float& theta, int limit,
-                                           int max_rows, int lane, bool exact_only) {
-  unsigned need = __ballot_sync(kFull, cnt > limit);
-  if (!need) return;
-  ulonglong2 raw[4];
-  load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * row_stride, raw, lane);
-  while (need && max_rows-- > 0) {
-    const int L = __ffs(need) - 1;
-    need &= need - 1;
-    ulonglong2 cur[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) cur[i] = raw[i];
-    if (need && max_rows > 0) load_keys_raw(warp_keys + size_t(__ffs(need) - 1) * row_stride, raw, lane);
-    int cntL = __shfl_sync(kFull, cnt, L);
-    float thL = __shfl_sync(kFull, theta, L);
-    prune_one(warp_keys + size_t(L) * row_stride, cur, cntL, thL, lane, exact_only);
-    if (lane == L) { cnt = cntL; theta = thL; }
-  }
-  __syncwarp();
-}
 
 // Merge of two descending-sorted 64-key lists into the best 64, descending.  Lanes 0-7 hold list A
 // (lane L: ranks 8L..8L+7); lanes 8-15 hold list B REVERSED (ascending over the 64 slots), so the 128 keys
@@ -339,6 +259,117 @@ __device__ __forceinline__ void warp_merge_best64_desc(uint64_t (&key)[8], int l
   }
 }
 
+// Threshold ladder.  A row's threshold must rise during the scan or every column would be appended, but finding
+// the row's current 64th best (sort / select over its key list) costs thousands of cycles per row on one warp and
+// made the slowest of the 16 warps that share an accumulator tile hold back the MMA pipe.  Instead every row
+// keeps three trial levels t1 < t2 < t3 above its threshold and counts, per 32-column chunk, whether the chunk
+// maximum exceeds each of them (one compare + one predicated add per level and chunk).  Every counted chunk holds
+// a distinct column above the level, and every such column is in the row's list, so once a level has been counted
+// kKeep times it is a certified threshold: theta moves up to it, the ladder shifts and a new top level is opened.
+// The spacing adapts so that the count roughly halves from level to level.  Nothing is sorted, re-read or
+// compacted during the scan; lists are simply long enough (kListCap) for the appends of a whole item, and the rare
+// list that does fill up is reduced to its exact best kKeep below (which also re-seeds the ladder from exact ranks).
+struct Ladder {
+  float t1, t2, t3, delta;
+  int c1, c2, c3;
+};
+__device__ __forceinline__ void ladder_restart(Ladder& ld, float theta) {
+  ld.delta = fmaxf(ld.delta, 1e-6f * fmaxf(1.f, fabsf(theta)));
+  ld.t1 = theta + ld.delta; ld.t2 = ld.t1 + ld.delta; ld.t3 = ld.t2 + ld.delta;
+  ld.c1 = ld.c2 = ld.c3 = 0;
+}
+__device__ __forceinline__ void ladder_off(Ladder& ld) {
+  ld.t1 = ld.t2 = ld.t3 = CUDART_INF_F; ld.delta = 0.f; ld.c1 = ld.c2 = ld.c3 = 0;
+}
+// per-lane slow path, entered when some lane has a certified or overtaken level
+__device__ __forceinline__ void ladder_step(Ladder& ld, float& theta, int cert) {
+  if (ld.c1 >= cert) {
+    theta = fmaxf(theta, ld.t1);
+    if (ld.c2 >= (3 * cert) / 4) ld.delta *= 1.5f;        // next level nearly certified too: levels too dense
+    else if (ld.c2 < (5 * cert) / 16) ld.delta *= 0.75f;  // far from it: too sparse
+    ld.delta = fmaxf(ld.delta, 1e-6f * fmaxf(1.f, fabsf(ld.t3)));
+    ld.t1 = ld.t2; ld.c1 = ld.c2; ld.t2 = ld.t3; ld.c2 = ld.c3;
+    ld.t3 = ld.t3 + ld.delta; ld.c3 = 0;
+  }
+  if (ld.t1 <= theta && theta > -CUDART_INF_F && ld.delta > 0.f) ladder_restart(ld, theta);   // adopted / pruned past the levels
+}
+
+// Exact reduction of one row's FULL key list `b` (cntL valid keys, up to kListCap) to its best kKeep = 64, written
+// back sorted; thL becomes the cert-th value.  lv = values at ranks 3c/4, c/2, c/4 (ladder seeds with those exact
+// counts).  The list is sorted 256 keys at a time and the running best 64 merged in.  All lanes pass the same arguments.
+__device__ __forceinline__ float rank_value(const uint64_t (&sorted)[8], int rank, int lane) {   // rank < 64, lanes 0-7 hold 8 each
+  uint64_t sel = 0ull;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) if (i == (rank & 7)) sel = sorted[i];
+  return key_val(shfl_u64(sel, rank >> 3));
+}
+__device__ __forceinline__ void prune_exact(uint64_t* b, int& cntL, float& thL, float (&lv)[3], int cert, int lane) {
+  uint64_t best[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) best[r] = 0ull;
+  for (int q0 = 0; q0 < cntL; q0 += kCap) {
+    uint64_t key[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = q0 + lane * 8 + 2 * i;
+      const ulonglong2 r = __ldcg(reinterpret_cast<const ulonglong2*>(b + e));
+      key[2 * i] = e < cntL ? r.x : 0ull;
+      key[2 * i + 1] = e + 1 < cntL ? r.y : 0ull;
+    }
+    warp_sort256_desc(key, lane);
+    if (q0 > 0) {
+      uint64_t rev[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) rev[r] = shfl_u64(key[7 - r], (15 - lane) & 31);   // lanes 8-15: this block's best 64, reversed
+#pragma unroll
+      for (int r = 0; r < 8; ++r) key[r] = lane < 8 ? best[r] : (lane < 16 ? rev[r] : 0ull);
+      warp_merge_best64_desc(key, lane);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) best[r] = key[r];
+  }
+  __syncwarp();
+  if (lane < kKeep / 8) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(best[i], best[i + 1]);
+  }
+  // cert columns >= the value at rank cert-1 stay in the list: that value is the new threshold
+  const float vth = rank_value(best, cert - 1, lane);
+  const float v1 = rank_value(best, (3 * cert) / 4 - 1, lane), v2 = rank_value(best, cert / 2 - 1, lane),
+              v3 = rank_value(best, cert / 4 - 1, lane);
+  if (cntL >= kKeep) {
+    thL = fmaxf(thL, vth); cntL = kKeep;
+    lv[0] = v1; lv[1] = v2; lv[2] = v3;
+  } else {
+    lv[0] = lv[1] = lv[2] = CUDART_INF_F;
+  }
+  __syncwarp();
+}
+
+// Reduces the lists of all lanes that are about to overflow (rare).
+__device__ __forceinline__ void prune_full_rows(uint64_t* warp_keys, size_t row_stride, int& cnt, float& theta, Ladder& ld,
+                                                int cert, int lane) {
+  unsigned need = __ballot_sync(kFull, cnt > kListCap - 32);
+  while (need) {
+    const int L = __ffs(need) - 1;
+    need &= need - 1;
+    int cntL = __shfl_sync(kFull, cnt, L);
+    float thL = __shfl_sync(kFull, theta, L);
+    float lv[3];
+    prune_exact(warp_keys + size_t(L) * row_stride, cntL, thL, lv, cert, lane);
+    if (lane == L) {
+      cnt = cntL; theta = thL;
+      if (lv[0] < CUDART_INF_F) {
+        ld.t1 = lv[0]; ld.t2 = lv[1]; ld.t3 = lv[2];
+        ld.c1 = (3 * cert) / 4; ld.c2 = cert / 2; ld.c3 = cert / 4;
+        ld.delta = fmaxf((lv[2] - lv[0]) * 0.625f, 1e-6f * fmaxf(1.f, fabsf(thL)));   // ranks 48 -> 16: 1.6 halvings
+      }
+    }
+  }
+  __syncwarp();
+}
+
 // Warp-wide bitonic sort of 32 floats (one per lane), descending: lane r ends up with rank r.
 __device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
 #pragma unroll
@@ -358,14 +389,16 @@ __device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
 // column, so a value with at least 64 recorded maxima >= it is a valid threshold (at least 64 columns beat it),
 // and it is nearly as tight as the true 64th best of those tiles.  The pivot comes from a sorted sample with
 // an exact count, as in prune_one.  The bootstrap tiles are re-scanned at the end of the item.
-__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, int nmax, float& theta, int lane) {
+__device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, int nmax, int cert, float& theta, float& delta,
+                                            int lane) {
   const bool two = nmax > 128;                       // 128 or 256 recorded maxima per row
   for (int L = 0; L < 32; ++L) {
     const float4* src = reinterpret_cast<const float4*>(warp_keys + size_t(L) * row_stride);
     const float4 v = __ldcg(src + lane);
     const float4 w = two ? __ldcg(src + 32 + lane) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
     const float s = warp_sort32_desc_f(v.x, lane);   // systematic sample: every 4th (8th) maximum
-    const int r0 = two ? 6 : 13, r1 = two ? 8 : 16, r2 = two ? 11 : 20;
+    // sample ranks around the cert-th of the recorded maxima (cert = 64: 13/16/20 of 32 samples, 6/8/11 with 256 maxima)
+    const int r0 = two ? cert / 8 - 2 : cert / 4 - 3, r1 = two ? cert / 8 : cert / 4, r2 = two ? cert / 8 + 3 : cert / 4 + 4;
     const float p0 = __shfl_sync(kFull, s, r0), p1 = __shfl_sync(kFull, s, r1), p2 = __shfl_sync(kFull, s, r2);
     int c0 = (v.x >= p0) + (v.y >= p0) + (v.z >= p0) + (v.w >= p0) + (w.x >= p0) + (w.y >= p0) + (w.z >= p0) + (w.w >= p0);
     int c1 = (v.x >= p1) + (v.y >= p1) + (v.z >= p1) + (v.w >= p1) + (w.x >= p1) + (w.y >= p1) + (w.z >= p1) + (w.w >= p1);
@@ -374,11 +407,14 @@ __device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t ro
     float mn = fminf(fminf(v.x, v.y), fminf(v.z, v.w));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
-    const float th = c0 >= kKeep ? p0 : (c1 >= kKeep ? p1 : (c2 >= kKeep ? p2 : mn));   // mn: 128 maxima >= it
+    const float th = c0 >= cert ? p0 : (c1 >= cert ? p1 : (c2 >= cert ? p2 : mn));   // mn: 128 maxima >= it
     // the filter keeps values STRICTLY above the threshold, and the >= 64 columns that certify `th` are only
     // collected later (re-scan): step one ulp down so that columns equal to `th` (mass ties!) are kept too
     const float th_open = __uint_as_float(f2ord_dec(th));
-    if (lane == L) theta = fmaxf(theta, th_open);
+    // ladder spacing: between the threshold (>= 64 maxima above) and a high sample rank (~12-14 above) the tail
+    // count drops ~4.6x = 2.2 halvings
+    const float qv = __shfl_sync(kFull, s, two ? 1 : (cert >= 48 ? 3 : 2));
+    if (lane == L) { theta = fmaxf(theta, th_open); delta = (qv - th) * (1.f / 2.2f); }
   }
 }
 
@@ -517,8 +553,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
-    const size_t row_stride = size_t(p.nseg) * kEpiGroups * kCap;     // keys between consecutive query rows
-    const bool exact_only = (p.debug & 4) != 0;
+    const size_t row_stride = size_t(p.nseg) * kEpiGroups * kListCap;     // keys between consecutive query rows
     const uint32_t tempty0 = (CG == 2) ? mapa_rank0(tmem_empty) : tmem_empty;
     uint32_t tc = 0, it = 0;
     for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
@@ -530,9 +565,11 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint64_t tag = uint64_t(uint32_t(item) + 1u) << 32;
       float theta = (p.debug & 2) ? CUDART_INF_F : -CUDART_INF_F;
       int cnt = 0;
+      Ladder ld;
+      ladder_off(ld);
       // this item's key buffers live in the output array: row-major [row][seg][group][kCap]
-      uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kCap) +
-                            size_t(grp) * kCap;
+      uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kListCap) +
+                            size_t(grp) * kListCap;
       uint64_t* my_keys = warp_keys + size_t(lane) * row_stride;
       const uint32_t keys_lo = uint32_t(reinterpret_cast<uintptr_t>(my_keys));
       th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
@@ -570,7 +607,9 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
           }
           if (bcount * (kGrpCols / 8) >= p.boot_tiles * 16) {   // all of this group's bootstrap tiles are recorded
-            boot_select(warp_keys, row_stride, p.boot_tiles * 16, theta, lane);
+            float delta = 0.f;
+            boot_select(warp_keys, row_stride, p.boot_tiles * 16, p.cert, theta, delta, lane);
+            if (!(p.debug & 2) && theta > -CUDART_INF_F) { ld.delta = fmaxf(delta, 0.f); ladder_restart(ld, theta); }
             __syncwarp();
             th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
             bcount = -1000000;
@@ -610,6 +649,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
             // warp-uniform gating (votes), so that groups without a survivor in ANY lane are really skipped
             if (__any_sync(kFull, mx > theta)) {
+              ld.c1 += mx > ld.t1; ld.c2 += mx > ld.t2; ld.c3 += mx > ld.t3;
+              if (__any_sync(kFull, ld.c1 >= p.cert || (ld.t1 <= theta && ld.delta > 0.f))) ladder_step(ld, theta, p.cert);
               const uint32_t nidx0 = ~uint32_t(colb + c);   // ~(idx0 + j) == ~idx0 - j
               uint64_t wp = reinterpret_cast<uint64_t>(my_keys + cnt);
 #pragma unroll
@@ -622,7 +663,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               cnt = int((uint32_t(wp) - keys_lo) >> 3);
             }
             __syncwarp();
-            if (__any_sync(kFull, cnt > kCap - 32)) prune_rows(warp_keys, row_stride, cnt, theta, kCap - 32, 32, lane, exact_only);   // must not overflow
+            if (__any_sync(kFull, cnt > kListCap - 32)) prune_full_rows(warp_keys, row_stride, cnt, theta, ld, p.cert, lane);   // must not overflow
           }
         }
         // publish this row's threshold and hand the accumulator buffer back to the MMA warp
@@ -633,10 +674,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           if (CG == 2) mbar_arrive_cluster(tempty0 + 8 * buf);
           else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tmem_empty + 8 * buf) : "memory");
         }
-        // deferred, rate-limited pruning: the accumulator buffer is already released, and at most a few rows
-        // are pruned per tile so that the correlated fill of the 32 rows does not turn into one long stall
-        prune_rows(warp_keys, row_stride, cnt, theta, p.soft_limit, p.prunes_per_tile, lane, exact_only);
-        th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
       }
       // ---- item done: the row's key buffer already sits in the output; publish its length and threshold.
       // (The exact top-64 selection over the union of the lists happens in the re-rank kernel, where thousands
@@ -687,7 +724,7 @@ static int make_map(lemon_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
 }
 
 template <int CG, int BN>
-static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg,
+static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg, int keep,
                      uint64_t* cand_keys, int32_t* cand_cnt, float* cand_theta, cudaStream_t stream) {
   const int kchunks = d16 / kBK;
   const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
@@ -710,11 +747,10 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   p.cand_keys = cand_keys; p.cand_cnt = cand_cnt; p.cand_theta = cand_theta;
   const char* dbg = getenv("LEMON_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
-  const char* e1 = getenv("LEMON_TC_SOFT");   p.soft_limit = e1 ? atoi(e1) : kSoftLimit;
-  const char* e2 = getenv("LEMON_TC_PPT");    p.prunes_per_tile = e2 ? atoi(e2) : kPrunesPerTile;
+  const char* e1 = getenv("LEMON_TC_CERT");   p.cert = e1 ? atoi(e1) : keep;     // experiments
+  if (p.cert < 8 || p.cert > kKeep) p.cert = keep;
   const char* e3 = getenv("LEMON_TC_BOOT");   p.boot_tiles = e3 ? atoi(e3) : kBootTiles;
   if (p.boot_tiles != 0 && p.boot_tiles != 8 && p.boot_tiles != 16) p.boot_tiles = kBootTiles;
-  if (p.soft_limit < 64 || p.soft_limit > kCap - 32) p.soft_limit = kSoftLimit;
 
   int64_t units = ctx->num_sms / CG;
   if (units > p.n_items) units = p.n_items;
@@ -744,15 +780,16 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
 }  // namespace lemon
 
 extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m,
-                                    int d16, int nseg, int cta_group, uint64_t* cand_keys, int32_t* cand_cnt,
+                                    int d16, int nseg, int cta_group, int keep, uint64_t* cand_keys, int32_t* cand_cnt,
                                     float* cand_theta, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
-      nseg < 1 || nseg > 64 || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
-      (uintptr_t(cand_keys) & (kCap * 8 - 1)))
-    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 2 KB-aligned cand_keys)", LEMON_MAX_D_TC);
+      nseg < 1 || nseg > 64 || keep < 0 || (keep > 0 && keep < 8) || keep > kKeep || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
+      (uintptr_t(cand_keys) & (kListCap * 8 - 1)))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 8 KB-aligned cand_keys)", LEMON_MAX_D_TC);
   if (nq == 0) return LEMON_OK;
+  if (keep == 0) keep = kKeep;
   if (cta_group == 0) cta_group = 2;   // CTA pairs: half the SMEM/L2 operand traffic per MMA
   cudaStream_t st = (cudaStream_t)stream;
   LEMON_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -760,12 +797,12 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
   int bn = bn_env ? atoi(bn_env) : 0;
   if (cta_group == 1) {
     if (bn == 0) bn = d16 <= 512 ? 256 : 128;
-    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
-    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
+    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
   }
   if (cta_group == 2) {
-    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
-    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, cand_keys, cand_cnt, cand_theta, st);
+    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
   }
   return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: cta_group must be 0, 1 or 2");
 }

@@ -8,21 +8,20 @@ namespace lemon {
 
 constexpr int kRrWarps = 8;
 
-// loads one chunk = two candidate lists (<= 2 x 256 keys, 16 per lane); invalid slots become 0
+// loads one chunk = 512 slots of a candidate list (16 keys per lane); invalid slots become 0
+constexpr int kRrChunk = 512;
+constexpr int kRrChunksPerList = kListCap / kRrChunk;
+static_assert(kListCap % kRrChunk == 0, "candidate lists are read in 512-key chunks");
 __device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_keys, const int32_t* __restrict__ cand_cnt,
                                            int64_t row, int nlist, int chunk, int lane, uint64_t (&k)[16], int& tot) {
-  tot = 0;
+  const int l = chunk / kRrChunksPerList, part = chunk % kRrChunksPerList;
+  const int c = max(0, min(min(cand_cnt[row * nlist + l], kListCap) - part * kRrChunk, kRrChunk));
+  tot = c;
+  const uint64_t* src = cand_keys + (row * nlist + l) * kListCap + part * kRrChunk;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int l = chunk * 2 + h;
-    const int c = l < nlist ? min(cand_cnt[row * nlist + l], kCap) : 0;
-    tot += c;
-    const uint64_t* src = cand_keys + (row * nlist + (l < nlist ? l : 0)) * kCap;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int e = i * 32 + lane;                    // coalesced: consecutive lanes read consecutive keys
-      k[h * 8 + i] = e < c ? __ldg(src + e) : 0ull;
-    }
+  for (int i = 0; i < 16; ++i) {
+    const int e = i * 32 + lane;                      // coalesced: consecutive lanes read consecutive keys
+    k[i] = e < c ? __ldg(src + e) : 0ull;
   }
 }
 
@@ -39,7 +38,7 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
   uint64_t* ebuf = sbuf[warp];
   uint64_t* cbuf = sbuf2[warp];
   const int64_t warps = int64_t(gridDim.x) * kRrWarps;
-  const int nchunk = (nlist + 1) >> 1;
+  const int nchunk = nlist * kRrChunksPerList;
   for (int64_t row = int64_t(blockIdx.x) * kRrWarps + warp; row < nq; row += warps) {
     const float* qr = q + row * d;
     // rounding-error bound of this row (include/lemon_b200.h)

@@ -31,7 +31,8 @@ int lemon_set_error(lemon_ctx* ctx, int code, const char* fmt, ...);
 
 namespace lemon {
 
-constexpr int kCap = 256;            // streaming top-k buffer entries per row
+constexpr int kCap = 256;            // keys one warp sorts at once (8 per lane); K2a staging capacity
+constexpr int kListCap = LEMON_LIST_CAP;   // slots per K1 candidate list
 constexpr int kKeep = LEMON_KPRIME;  // survivors per compaction (k')
 constexpr unsigned kFull = 0xffffffffu;
 

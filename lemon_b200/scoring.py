@@ -17,7 +17,7 @@ from . import _lib
 
 HP_KEYS = ("beta", "gamma", "tau_1_n", "tau_2_n", "tau_1_m", "tau_2_m")
 KPRIME = 64
-LIST_CAP = 256
+LIST_CAP = 1024
 MAX_KP = 64
 MAX_D_TC = 768
 # bound on the fp32 accumulation error of the tensor-core inner product (|q|,|b| <= ~1);
@@ -85,6 +85,12 @@ def decode_candidates(cand_keys: torch.Tensor, cand_cnt: torch.Tensor, n_rows: i
     idx = np.where(valid, idx, -1).reshape(n, -1)
     order = np.lexsort((idx, -vals), axis=1)
     return np.take_along_axis(vals, order, 1), np.take_along_axis(idx, order, 1)
+
+
+def tc_keep(kp: int) -> int:
+    """Columns every K1 list certifies above its threshold: the top kp plus a margin for the fp16 rounding
+    error (the re-rank certificate decides; rows it cannot certify take the exact kernel)."""
+    return int(min(MAX_KP, max(32, kp + 9)))
 
 
 def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
@@ -242,7 +248,8 @@ class LemonScorer:
                                                     _stream()), "lemon_knn_exact")
         return top
 
-    def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None):
+    def knn_candidates(self, q: Prepared, db: Prepared, nseg: int | None = None, cta_group: int | None = None,
+                       keep: int = 0):
         """K1.  Returns (cand_keys int64[nq_pad, nlist, 256] (uint64 bit patterns), cand_cnt int32[nq_pad, nlist],
         cand_theta fp32[nq_pad, nlist], nseg) with nlist = 2*nseg; see include/lemon_b200.h."""
         cg = self.cta_group if cta_group is None else cta_group
@@ -250,7 +257,7 @@ class LemonScorer:
             nseg = plan_segments(q.n, db.n, self.num_sms, cg if cg else 2, db.d16)
         nlist = 2 * nseg
         nq_pad = -(-q.n // 256) * 256
-        # K1 addresses a row's 2 KB key list with a 32-bit pointer bump: the array must be 2 KB-aligned
+        # K1 addresses a row's 8 KB key list with a 32-bit pointer bump: the array must be 8 KB-aligned
         raw = torch.empty(nq_pad * nlist * LIST_CAP + LIST_CAP, dtype=torch.int64, device=self.device)
         skip = (-raw.data_ptr() % (LIST_CAP * 8)) // 8
         cand_keys = raw[skip: skip + nq_pad * nlist * LIST_CAP].view(nq_pad, nlist, LIST_CAP)
@@ -262,7 +269,7 @@ class LemonScorer:
             ev[0].record()
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_knn_candidates(self.ctx.handle, _ptr(q.f16), _ptr(db.f16), q.n, db.n, db.d16,
-                                                         nseg, cg, _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
+                                                         nseg, cg, keep, _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
                                                          _stream()), "lemon_knn_candidates")
         if ev is not None:
             ev[1].record()
@@ -320,7 +327,7 @@ class LemonScorer:
         n_uncs, nsegs = [], []
         for r0, r1, ns in parts:
             qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)
-            *cand, nseg = self.knn_candidates(qs, db, nseg=ns)
+            *cand, nseg = self.knn_candidates(qs, db, nseg=ns, keep=tc_keep(kp))
             tv, ti = top_val[r0:r1], top_idx[r0:r1]
             _, _, uncert, n_unc = self.rerank(qs, db, cand, kp, metric, out=(tv, ti))
             # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the

@@ -174,11 +174,11 @@ def test_tc_candidates_match_fp16_matmul(lb, cg, nq, m, d, nseg):
     sc = lb.get_scorer()
     qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
     ck, cc, ct, nseg_out = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
-    assert nseg_out == nseg and ck.shape[1:] == (2 * nseg, 256) and ck.shape[0] % 256 == 0
+    assert nseg_out == nseg and ck.shape[1:] == (2 * nseg, 1024) and ck.shape[0] % 256 == 0
     S = (qp.f16.float() @ dbp.f16.float().T).cpu().numpy()
     cv, ci = decode_candidates(ck, cc, nq)
     valid = ci >= 0
-    assert (ci < m).all() and (cc[:nq].cpu().numpy() <= 256).all()
+    assert (ci < m).all() and (cc[:nq].cpu().numpy() <= 1024).all()
     for r in (0, nq // 2, nq - 1):                                # no duplicate columns inside a row
         v = ci[r][valid[r]]
         assert len(np.unique(v)) == len(v)

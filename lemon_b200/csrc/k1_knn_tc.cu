@@ -33,6 +33,7 @@ constexpr int kMaxSmem = 232448;               // 227 KB
 struct TcParams {
   int64_t nq, m;
   int kchunks;          // d16 / 64
+  int kres;             // query-tile K chunks resident in SMEM for the whole scan (the rest stream through the ring)
   int nseg;
   int64_t seg_len;      // columns per segment (multiple of BN)
   int nstage;
@@ -445,7 +446,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   const int kBoot = p.boot_tiles * 256 / BN;       // bootstrap tiles per item: 128 (or 256) group maxima per epilogue group
 
   const uint32_t a_smem = smem_base;
-  const uint32_t b_smem = a_smem + uint32_t(p.kchunks) * kAChunkBytes;
+  const uint32_t b_smem = a_smem + uint32_t(p.kres) * kAChunkBytes;
   const uint32_t bar_base = b_smem + uint32_t(p.nstage) * kStageBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.nstage + s); };
@@ -489,14 +490,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int row0 = int(rt * (kBM * CG) + cta_rank * kBM);
         // query tile: wait until the previous item's MMAs have drained it
         mbar_wait(a_empty, (it & 1) ^ 1);
-        if (cta_rank == 0) mbar_arrive_expect_tx(a_full, uint32_t(p.kchunks) * kAChunkBytes * CG);
-        for (int kc = 0; kc < p.kchunks; ++kc)
+        if (cta_rank == 0) mbar_arrive_expect_tx(a_full, uint32_t(p.kres) * kAChunkBytes * CG);
+        for (int kc = 0; kc < p.kres; ++kc)
           tma_load_2d<CG>(a_smem + kc * kAChunkBytes, &map_q, afull_l, kc * kBK, row0);
         const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);   // bootstrap tiles are scanned twice
         for (int64_t i = 0; i < nsteps; ++i) {
           const int64_t t = i < ntiles ? i : i - ntiles;
           const int dbrow = int(col0 + t * BN + cta_rank * kBRows);
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            if (kc >= p.kres) {   // non-resident query chunk: one ring stage (same size as a DB stage)
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), kAChunkBytes * CG);
+              tma_load_2d<CG>(b_smem + stage * kStageBytes, &map_q, full0 + 8u * stage, kc * kBK, row0);
+              if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
             mbar_wait(empty_bar(stage), phase ^ 1);
             if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), kStageBytes * CG);
             tma_load_2d<CG>(b_smem + stage * kStageBytes, &map_db, full0 + 8u * stage, kc * kBK, dbrow);
@@ -525,13 +532,22 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kc = 0; kc < p.kchunks; ++kc) {
+            uint32_t a_addr = a_smem + kc * kAChunkBytes;
+            int a_stage = -1;
+            if (kc >= p.kres) {                      // streamed query chunk
+              mbar_wait(full_bar(stage), phase);
+              a_stage = stage;
+              a_addr = b_smem + stage * kStageBytes;
+              if (++stage == p.nstage) { stage = 0; phase ^= 1; }
+            }
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
-            const uint64_t adesc = make_smem_desc(a_smem + kc * kAChunkBytes);
+            const uint64_t adesc = make_smem_desc(a_addr);
             const uint64_t bdesc = make_smem_desc(b_smem + stage * kStageBytes);
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 16; ++k4)   // +32 B per UMMA_K inside the 128 B swizzle row
               umma_f16<CG>(d_tmem, adesc + uint64_t(2 * k4), bdesc + uint64_t(2 * k4), idesc, (kc | k4) != 0);
+            if (a_stage >= 0) umma_commit<CG>(empty_bar(a_stage));
             umma_commit<CG>(empty_bar(stage));       // frees the DB stage (both CTAs)
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           }
@@ -727,8 +743,19 @@ template <int CG, int BN>
 static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg, int keep,
                      uint64_t* cand_keys, int32_t* cand_cnt, float* cand_theta, cudaStream_t stream) {
   const int kchunks = d16 / kBK;
-  const uint32_t a_bytes = uint32_t(kchunks) * kAChunkBytes;
   const uint32_t stage_bytes = (BN / CG) * kBK * 2;
+  // Query-tile residency: all K chunks stay in SMEM when that leaves a ring of >= 4 DB stages; otherwise (d16 > 640)
+  // the last chunks are re-streamed through the ring with every DB tile -- a 2-stage ring (32 KB in flight per CTA)
+  // cannot cover the L2 latency, 4 stages can, at the price of 17 % more L2 -> SMEM traffic (d16 = 768: 10 of 12
+  // chunks resident; measured 907 -> 1082 TFLOP/s on a 50000 x 400000 x 768 launch; 9 / 8 / 6 resident: 1064 / 1042 / 1016).
+  int kres = kchunks;
+  if (stage_bytes == uint32_t(kAChunkBytes)) {
+    const int fit = int((int64_t(kMaxSmem) - 2368 - 4 * int64_t(stage_bytes)) / kAChunkBytes);
+    if (fit < kres) kres = fit < 1 ? 1 : fit;
+    const char* e0 = getenv("LEMON_TC_KRES");       // experiments
+    if (e0 && atoi(e0) >= 1 && atoi(e0) <= kchunks) kres = atoi(e0);
+  }
+  const uint32_t a_bytes = uint32_t(kres) * kAChunkBytes;
   // dynamic shared memory starts 1024-aligned (no static __shared__ in this kernel; checked on the device)
   const int64_t avail = int64_t(kMaxSmem) - 2368 /*barriers + threshold exchange*/ - a_bytes;
   int nstage = int(avail / stage_bytes);
@@ -737,7 +764,7 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const size_t smem = a_bytes + size_t(nstage) * stage_bytes + 2368;
 
   TcParams p;
-  p.nq = nq; p.m = m; p.kchunks = kchunks; p.nstage = nstage;
+  p.nq = nq; p.m = m; p.kchunks = kchunks; p.kres = kres; p.nstage = nstage;
   int64_t seg_len = (m + nseg - 1) / nseg;
   seg_len = (seg_len + BN - 1) / BN * BN;
   // segments past the end of the DB are legal: they emit empty (-inf, -1) lists

@@ -11,7 +11,7 @@ constexpr int kScWarps = 8;
 struct ScoreHp { double beta, gamma, t1n, t2n, t1m, t2m; int has; };
 
 template <int METRIC>
-__global__ void __launch_bounds__(kScWarps * 32)
+__global__ void __launch_bounds__(kScWarps * 32, 3)
 score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const float* __restrict__ xdb,
              const float* __restrict__ ydb, const float* __restrict__ dists_tr, const float* __restrict__ topn_val,
              const int32_t* __restrict__ topn_idx, const float* __restrict__ topm_val,
@@ -189,7 +189,7 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "score: bad args (kp must be k+1 with query_in_db, k without)");
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kScWarps - 1) / kScWarps;
-  const int64_t cap = int64_t(ctx->num_sms) * 8;
+  const int64_t cap = int64_t(ctx->num_sms) * 6;   // 3 resident blocks per SM (<= 80 registers), two waves
   if (blocks > cap) blocks = cap;
   const ScoreHp h = make_hp(hp);
   if (metric == LEMON_METRIC_IP)

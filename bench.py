@@ -195,7 +195,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("LEMON_BENCH_WORKLOAD", "c2"), choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="lemon_b200", choices=["lemon_b200", "reference"])
     ap.add_argument("--ref-queries", type=int, default=1024)
-    ap.add_argument("--cpu-queries", type=int, default=2048)
+    ap.add_argument("--cpu-queries", type=int, default=16384)   # ~15 s of host work on the bench box
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

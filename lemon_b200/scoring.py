@@ -139,6 +139,32 @@ def plan_tail(nq: int, m: int, num_sms: int, cta_group: int) -> tuple[int, int]:
     return full * rows_per_tile, nseg
 
 
+def plan_parts(nq: int, m: int, num_sms: int, cta_group: int, max_rows: int = 1 << 19) -> list[tuple[int, int, int | None]]:
+    """K1 launches of one kNN call as (row0, row1, nseg or None = planner's choice).  The main part is cut into
+    whole rounds of query tiles (one round = one 128*cta_group-row tile per CTA pair, so every cut launch is as
+    efficient as the uncut one) of at most `max_rows` rows: a launch's candidate lists take 2 * 8 KB per row, which
+    bounds them to ~8.6 GB however many query rows there are.  The tail part comes from plan_tail."""
+    n_main, nseg_tail = plan_tail(nq, m, num_sms, cta_group)
+    round_rows = max(1, num_sms // cta_group) * 128 * cta_group
+    step = max(1, max_rows // round_rows) * round_rows
+    parts: list[tuple[int, int, int | None]] = []
+    if n_main >= nq:
+        cuts = list(range(0, nq, step)) + [nq]
+        if len(cuts) > 2 and cuts[-1] - cuts[-2] < round_rows:      # do not leave a short last launch
+            del cuts[-2]
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            parts.append((a, b, None if len(cuts) == 2 else 1))
+        if len(parts) > 1:                                          # the last piece may again want a tail split
+            a, b, _ = parts.pop()
+            nm2, ns2 = plan_tail(b - a, m, num_sms, cta_group)
+            parts += [(a, b, None)] if nm2 >= b - a else [(a, a + nm2, 1), (a + nm2, b, ns2)]
+        return parts
+    for a in range(0, n_main, step):
+        parts.append((a, min(a + step, n_main), 1))
+    parts.append((n_main, nq, nseg_tail))
+    return parts
+
+
 class LemonScorer:
     """Drop-in engine for the scoring path.  Mirrors the order of run_lemon.py:
     ``set_database`` == lines 163-176 (normalise, dists_tr, index.add),
@@ -322,8 +348,7 @@ class LemonScorer:
         top_val = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
         top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
         cg = self.cta_group if self.cta_group else 2
-        n_main, nseg_tail = plan_tail(q.n, db.n, self.num_sms, cg)
-        parts = [(0, q.n, None)] if n_main >= q.n else [(0, n_main, 1), (n_main, q.n, nseg_tail)]
+        parts = plan_parts(q.n, db.n, self.num_sms, cg)
         n_uncs, nsegs = [], []
         for r0, r1, ns in parts:
             qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)

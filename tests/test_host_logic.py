@@ -81,3 +81,21 @@ def test_plan_tail():
     assert plan_tail(74 * 256 + 60 * 256, 118_000, 148, 2)[1] == 1             # tail nearly a full round: leave it
     n_main, nseg = plan_tail(118_000, 10_000, 148, 2)
     assert nseg == 2 and 10_000 // nseg >= 4096                                # short DB: fewer segments
+
+
+def test_plan_parts_bounds_candidate_memory():
+    """K1 launches of one kNN call: contiguous cover of the rows, whole rounds of query tiles per cut, at most
+    2**19 rows (8.6 GB of candidate lists) per launch; small problems stay one launch as planned by plan_tail."""
+    from lemon_b200.scoring import plan_parts, plan_tail
+    assert plan_parts(118_000, 118_000, 148, 2) == [(0, 6 * 74 * 256, 1), (6 * 74 * 256, 118_000, 4)]   # C2 unchanged
+    assert plan_parts(1000, 5000, 148, 2) == [(0, 1000, None)]
+    assert plan_parts(412_500, 3_300_000, 148, 2) == [(0, 412_500, None)]                              # C4 on 8 GPUs
+    for nq, m in ((3_300_000, 3_300_000), (18944 * 27 + 5, 100_000), (18944 * 30, 1_000_000), (600_000, 50_000)):
+        parts = plan_parts(nq, m, 148, 2)
+        assert parts[0][0] == 0 and parts[-1][1] == nq
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(b - a <= (1 << 19) + 18944 for a, b, _ in parts)
+        assert all((b - a) % 18944 == 0 for a, b, _ in parts[:-2])                                     # whole rounds
+        n_main, nseg_tail = plan_tail(nq, m, 148, 2)
+        if n_main < nq:
+            assert parts[-1] == (n_main, nq, nseg_tail)

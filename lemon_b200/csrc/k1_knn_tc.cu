@@ -223,7 +223,7 @@ __device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
 }
 
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
-constexpr int kBootMinTiles = 64;              // items shorter than this run without the bootstrap
+constexpr int kBootMinTiles = 16;              // items shorter than this run without the bootstrap (their lists fill up once and are reduced exactly)
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g scans column half g of every accumulator tile
 
 // Merge of two descending-sorted 64-key lists into the best 64, descending.  Lanes 0-7 hold list A

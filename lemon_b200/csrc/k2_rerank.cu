@@ -7,6 +7,7 @@
 namespace lemon {
 
 constexpr int kRrWarps = 8;
+constexpr int kSelCap = 1024;            // selection buffer (keys) per warp; a chunk adds at most kRrChunk = 512
 
 // loads one chunk = 512 slots of a candidate list (16 keys per lane); invalid slots become 0
 constexpr int kRrChunk = 512;
@@ -32,11 +33,12 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
               const float* __restrict__ q_row_stats, const float* __restrict__ db_stats_max, float acc_eps, int64_t nq,
               int64_t m, int d, int nlist, int kp, float* __restrict__ top_val, int32_t* __restrict__ top_idx,
               int32_t* __restrict__ uncert_rows, int32_t* __restrict__ n_uncert) {
-  __shared__ uint64_t sbuf[kRrWarps][kCap];
-  __shared__ uint64_t sbuf2[kRrWarps][kCap];
+  // per warp: selection buffer (kSelCap keys: all candidates above the bound that may still be in the top-kp) and
+  // the exact keys of the gathered candidates (kCap)
+  extern __shared__ __align__(16) unsigned char rr_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint64_t* ebuf = sbuf[warp];
-  uint64_t* cbuf = sbuf2[warp];
+  uint64_t* cbuf = reinterpret_cast<uint64_t*>(rr_smem) + size_t(warp) * (kSelCap + kCap);
+  uint64_t* ebuf = cbuf + kSelCap;
   const int64_t warps = int64_t(gridDim.x) * kRrWarps;
   const int nchunk = nlist * kRrChunksPerList;
   for (int64_t row = int64_t(blockIdx.x) * kRrWarps + warp; row < nq; row += warps) {
@@ -49,53 +51,79 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
       qsq = st.w;
       dbdev = db_stats_max[3];
     }
-    // ---- 1. B = bound on every column that is in no list; lb = a lower bound of the kp-th best approximate
-    //         value: a value with at least kp candidates >= it, found by bisection on the ordered bit pattern
+    // ---- 1. B = bound on every column that is in no list
     float B = -CUDART_INF_F;
     for (int l = lane; l < nlist; l += 32) B = fmaxf(B, cand_theta[row * nlist + l]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) B = fmaxf(B, __shfl_xor_sync(kFull, B, o));
-    uint32_t lb = 0u;                                   // ordered bits; 0 is below every real value
+    // ---- 2. streaming selection over the UNION of the row's lists.  A certified top-kp has exact values > B + eps,
+    //         hence approximate values > B: only keys above B are collected.  Whenever the buffer passes half its
+    //         capacity, `sel` = (a lower bound of) the kp-th best key collected so far is found by bisection on the
+    //         ordered bit pattern and everything below it is dropped; at the end `sel` is a lower bound of the kp-th
+    //         best approximate value of the whole row however many lists (segments) there are.
+    //         Keys within `margin` (twice the rounding bound) below `sel` stay: their exact value may still be in the top-kp.
+    const float margin = 2.f * eps + (METRIC == LEMON_METRIC_L2 ? dbdev : 0.f);
+    const uint32_t above_B = f2ord(B) + 1u;           // keys must be strictly above B (f2ord(-inf) + 1 is still tiny)
+    uint32_t sel = 0u, keep_bits = above_B;
+    int n = 0;
+    bool overflow = false;
+    auto compact_ge = [&](uint32_t lo_bits, float minval) {      // keep keys with ordered value >= lo_bits and value >= minval
+      int w = 0;
+      for (int s0 = 0; s0 < n; s0 += 32) {
+        const int e = s0 + lane;
+        const uint64_t key = e < n ? cbuf[e] : 0ull;
+        const bool keep = key != 0ull && uint32_t(key >> 32) >= lo_bits && key_val(key) >= minval;
+        const unsigned mask = __ballot_sync(kFull, keep);
+        __syncwarp();
+        if (keep) cbuf[w + __popc(mask & ((1u << lane) - 1u))] = key;     // w + rank <= e: in-place is safe
+        w += __popc(mask);
+      }
+      __syncwarp();
+      n = w;
+    };
+    auto kth_lower_bound = [&]() -> uint32_t {                  // a value with at least kp collected keys >= it (n >= kp)
+      uint32_t lo = 0xffffffffu, hi = 0u;
+      for (int e = lane; e < n; e += 32) { const uint32_t o = uint32_t(cbuf[e] >> 32); lo = min(lo, o); hi = max(hi, o); }
+      lo = __reduce_min_sync(kFull, lo);
+      hi = __reduce_max_sync(kFull, hi);              // count(>= lo) = n >= kp ; count(>= hi + 1) = 0
+      for (int it = 0; it < 14 && hi > lo; ++it) {
+        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+        int cge = 0;
+        for (int e = lane; e < n; e += 32) cge += uint32_t(cbuf[e] >> 32) >= mid;
+        cge = __reduce_add_sync(kFull, cge);
+        if (cge >= kp) lo = mid; else hi = mid - 1u;
+      }
+      return lo;
+    };
     uint64_t k[16];
     int tot;
     for (int c = 0; c < nchunk; ++c) {
       load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
-      if (tot < kp) continue;
-      uint32_t lo = 0xffffffffu, hi = 0u;
+      if (tot == 0) continue;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const uint32_t o = uint32_t(k[i] >> 32);
-        if (k[i] != 0ull) { lo = min(lo, o); hi = max(hi, o); }
+        const bool pred = k[i] != 0ull && uint32_t(k[i] >> 32) >= keep_bits && uint32_t(key_idx(k[i])) < uint32_t(m);
+        const unsigned mask = __ballot_sync(kFull, pred);
+        const int pos = n + __popc(mask & ((1u << lane) - 1u));
+        if (pred && pos < kSelCap) cbuf[pos] = k[i];
+        n += __popc(mask);
       }
-      lo = __reduce_min_sync(kFull, lo);
-      hi = __reduce_max_sync(kFull, hi);               // count(>= lo) = tot >= kp ; count(>= hi + 1) = 0
-      for (int it = 0; it < 12 && hi > lo; ++it) {
-        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
-        int cge = 0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) cge += (k[i] != 0ull) && (uint32_t(k[i] >> 32) >= mid);
-        cge = __reduce_add_sync(kFull, cge);
-        if (cge >= kp) lo = mid; else hi = mid - 1u;
+      if (n > kSelCap) { overflow = true; n = kSelCap; }
+      __syncwarp();
+      if (n > kSelCap / 2 && n >= kp) {               // room for the next chunk (<= kRrChunk keys)
+        sel = max(sel, kth_lower_bound());
+        keep_bits = max(above_B, f2ord(ord2f(sel) - margin));
+        compact_ge(keep_bits, -CUDART_INF_F);
+        if (n > kSelCap / 2) overflow = true;         // mass ties around the kp-th value: the exact kernel takes the row
       }
-      lb = max(lb, lo);
     }
+    __syncwarp();
+    const uint32_t lb = n >= kp ? max(sel, kth_lower_bound()) : 0u;
     // the kp candidates above lb certify kp elements with exact value >= lb - eps, so a candidate whose
     // approximate value is below lb - 2 eps cannot be in the exact top-kp and is not gathered
-    const float cut = lb ? ord2f(lb) - 2.f * eps - (METRIC == LEMON_METRIC_L2 ? dbdev : 0.f) : -CUDART_INF_F;
-    // ---- 2. stage the surviving candidates (shared memory), then evaluate them exactly, four at a time
-    int ccnt = 0;
-    bool overflow = false;
-    for (int c = 0; c < nchunk; ++c) {
-      if (nchunk > 1 || c > 0) load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const bool pred = k[i] != 0ull && key_val(k[i]) >= cut && uint32_t(key_idx(k[i])) < uint32_t(m);
-        const unsigned mask = __ballot_sync(kFull, pred);
-        const int pos = ccnt + __popc(mask & ((1u << lane) - 1u));
-        if (pred && pos < kCap) cbuf[pos] = k[i];
-        ccnt += __popc(mask);
-      }
-    }
+    const float cut = lb ? ord2f(lb) - margin : -CUDART_INF_F;
+    compact_ge(0u, cut);
+    int ccnt = n;
     if (ccnt > kCap) { overflow = true; ccnt = kCap; }
     __syncwarp();
     const int ecnt = ccnt;
@@ -168,12 +196,15 @@ extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, con
   int64_t blocks = (nq + kRrWarps - 1) / kRrWarps;
   const int64_t cap = int64_t(ctx->num_sms) * 8;
   if (blocks > cap) blocks = cap;
+  const size_t smem = size_t(kRrWarps) * (kSelCap + kCap) * sizeof(uint64_t);     // 80 KB: two blocks per SM
+  LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(rerank_kernel<LEMON_METRIC_IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(rerank_kernel<LEMON_METRIC_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (metric == LEMON_METRIC_IP)
-    rerank_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kRrWarps * 32, 0, (cudaStream_t)stream>>>(
+    rerank_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kRrWarps * 32, smem, (cudaStream_t)stream>>>(
         q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, top_val, top_idx,
         uncert_rows, n_uncert);
   else
-    rerank_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kRrWarps * 32, 0, (cudaStream_t)stream>>>(
+    rerank_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kRrWarps * 32, smem, (cudaStream_t)stream>>>(
         q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, top_val, top_idx,
         uncert_rows, n_uncert);
   ctx->launches++;

@@ -292,7 +292,18 @@ __device__ __forceinline__ void ladder_step(Ladder& ld, float& theta, int cert) 
     ld.t1 = ld.t2; ld.c1 = ld.c2; ld.t2 = ld.t3; ld.c2 = ld.c3;
     ld.t3 = ld.t3 + ld.delta; ld.c3 = 0;
   }
-  if (ld.t1 <= theta && theta > -CUDART_INF_F && ld.delta > 0.f) ladder_restart(ld, theta);   // adopted / pruned past the levels
+  if (theta > -CUDART_INF_F && ld.delta > 0.f) {
+    // levels overtaken by a threshold adopted from the other epilogue group: drop them but keep the counts of the
+    // levels that are still above it; restart only when the whole ladder has been passed
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      if (ld.t1 <= theta) {
+        ld.t1 = ld.t2; ld.c1 = ld.c2; ld.t2 = ld.t3; ld.c2 = ld.c3;
+        ld.t3 = ld.t3 + ld.delta; ld.c3 = 0;
+      }
+    }
+    if (ld.t1 <= theta) ladder_restart(ld, theta);
+  }
 }
 
 // Exact reduction of one row's FULL key list `b` (cntL valid keys, up to kListCap) to its best kKeep = 64, written

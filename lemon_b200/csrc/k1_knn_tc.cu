@@ -11,9 +11,9 @@
 //                             (so a buffer is held for half a scan time and no group idles while "its" buffer
 //                             is being refilled).  tcgen05.ld 32x32b (thread == query row), FMNMX3 max tree
 //                             against the row's threshold, survivors appended branch-free as 64-bit keys to the
-//                             row's 256-slot list (which lives in the OUTPUT array), sample-pivot pruning
-//                             deferred until the TMEM buffer is handed back, thresholds shared between the
-//                             groups, threshold bootstrap from group maxima.
+//                             row's 1024-slot list (which lives in the OUTPUT array); the row thresholds rise by
+//                             a counting ladder (no sorting or compaction during the scan), are shared between
+//                             the groups and bootstrapped from group maxima.
 // Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
 // in the same order and DB tiles are served from L2.  The union / top-64 selection over a row's lists
 // is done by the re-rank kernel (k2_rerank.cu).
@@ -207,21 +207,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // ---------------------------------------------------------------- streaming top-k (epilogue)
-// Warp-wide bitonic sort of 32 keys (one per lane), descending: lane r ends up with rank r.
-__device__ __forceinline__ uint64_t warp_sort32_desc(uint64_t key, int lane) {
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const uint64_t o = shfl_xor_u64(key, j);
-      const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
-      const uint64_t mx = key > o ? key : o, mn = key > o ? o : key;
-      key = keep_max ? mx : mn;
-    }
-  }
-  return key;
-}
-
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
 constexpr int kBootMinTiles = 16;              // items shorter than this run without the bootstrap (their lists fill up once and are reduced exactly)
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g scans column half g of every accumulator tile
@@ -400,7 +385,7 @@ __device__ __forceinline__ float warp_sort32_desc_f(float x, int lane) {
 // (128 floats per row, kept in the row's still unused key buffer).  Every group maximum is a distinct DB
 // column, so a value with at least 64 recorded maxima >= it is a valid threshold (at least 64 columns beat it),
 // and it is nearly as tight as the true 64th best of those tiles.  The pivot comes from a sorted sample with
-// an exact count, as in prune_one.  The bootstrap tiles are re-scanned at the end of the item.
+// an exact count.  The bootstrap tiles are re-scanned at the end of the item.
 __device__ __forceinline__ void boot_select(const uint64_t* warp_keys, size_t row_stride, int nmax, int cert, float& theta, float& delta,
                                             int lane) {
   const bool two = nmax > 128;                       // 128 or 256 recorded maxima per row
@@ -482,9 +467,6 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-
-  const int64_t n_row_tiles = p.n_items / p.nseg;
-  (void)n_row_tiles;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -575,8 +557,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     // same query rows; each keeps its own key buffer and they exchange thresholds through shared memory (a
     // threshold certified by either group is a valid filter for both).
     const int grp = (warp - 4) >> 2;
-    const bool one_group = false;
-    if (!(one_group && grp == 1)) {
+    {
     const int quad = warp & 3;
     const int row_local = quad * 32 + lane;
     const uint32_t tmem_lane = uint32_t(quad * 32) << 16;
@@ -645,7 +626,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         {   // adopt the other group's threshold for this row if it is tighter (same item only)
           const uint64_t o = th_sh[(grp ^ 1) * kBM + row_local];
-          if (!one_group && (o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
+          if ((o >> 32) == (tag >> 32)) theta = fmaxf(theta, __uint_as_float(uint32_t(o)));
         }
         const int64_t colb = col0 + t * BN + grp * kGrpCols;          // this group's half of the tile
         const int valid = int(max(int64_t(0), min(int64_t(kGrpCols), col1 - colb)));
@@ -712,7 +693,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
       __syncwarp();
     }
-    }   // !(one_group && grp == 1)
+    }
   }
 
   // =============================== teardown ===============================

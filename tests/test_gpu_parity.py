@@ -464,3 +464,35 @@ def test_fuzz_shapes_default_path_equals_exact_and_oracle(lb, seed):
         assert r["wrong"] == 0, (m, nq, d, kp, metric, r["wrong_rows"][:3])
     else:
         assert (got[:, m:] == -1).all() and (np.sort(got[:, :m], 1) == np.arange(m)).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,nseg,keep", [(40_000, 8, 40), (20_000, 8, 40), (40_000, 8, 64), (30_000, 16, 32)])
+def test_many_segments_stay_certified(lb, m, nseg, keep):
+    """A tail launch splits the DB into up to 8 segments = 16 candidate lists per row, each certifying only its own
+    `keep` best.  The re-rank selects over the UNION of the lists, so the rows stay certified (no exact fallback)
+    and equal the brute-force kernel bit for bit.  (A per-list bound left > 256 candidates per row here and sent
+    every tail row of a 2-GPU C2 run to the exact kernel.)  m = 20000 runs without the threshold bootstrap, so
+    every list fills up once and goes through the exact reduction."""
+    import torch
+    sc = lb.get_scorer()
+    d, kp, nq = 128, 31, 900
+    x, _, _, _ = clustered_pairs(m, d, n_clusters=m // 150, seed=5)
+    qp, dbp = sc.prepare(x[:nq].copy(), True), sc.prepare(x, True)
+    ck, cc, ct, ns = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=2, keep=keep)
+    assert ns == nseg and ck.shape[1] == 2 * nseg and int(cc[:nq].max()) <= 1024
+    tv, ti, uncert, n_unc = sc.rerank(qp, dbp, (ck, cc, ct), kp, 0)
+    ev, ei = sc.knn_exact(qp, dbp, kp, 0)
+    torch.cuda.synchronize()
+    assert int(n_unc.item()) == 0
+    assert bool((ti == ei).all()) and bool((tv == ev).all())
+    # the two lists of a segment (one per epilogue group; they adopt each other's thresholds) together hold at
+    # least `keep` columns at or above the larger of their two thresholds
+    k64 = ck[:nq].cpu().numpy().view(np.uint64)
+    hi = (k64 >> np.uint64(32)).astype(np.uint32)
+    vals = np.where(hi >> 31, hi ^ np.uint32(0x80000000), ~hi).view(np.float32)
+    cnt, th = cc[:nq].cpu().numpy(), ct[:nq].cpu().numpy()
+    valid = np.arange(1024)[None, None, :] < cnt[:, :, None]
+    th_seg = th.reshape(nq, nseg, 2).max(-1)                                  # [nq, nseg]
+    above = (valid & (vals >= np.repeat(th_seg, 2, axis=1)[:, :, None])).sum(-1).reshape(nq, nseg, 2).sum(-1)
+    assert (above[np.isfinite(th_seg)] >= keep).all()

@@ -84,7 +84,7 @@ int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* ou
  *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. LEMON_LIST_CAP);
  *     cand_theta [nq_pad, nseg*2] fp32: every DB column of that list's share of the scan that is NOT in the list
  *                has approximate inner product <= theta (-inf: the list holds everything it saw).
- *   keep (8 .. LEMON_KPRIME; 0 = LEMON_KPRIME): the two lists of a segment together hold at least `keep` columns at
+ *   keep (16 .. LEMON_KPRIME; 0 = LEMON_KPRIME): the two lists of a segment together hold at least `keep` columns at
  *   or above the larger of their two cand_theta values (when the segment is long enough to have a threshold at all),
  *   so together the lists of a row contain its `keep` best approximate inner products (ties: lower DB rows first).  A smaller `keep` means fewer appended keys; callers that need the top kp choose
  *   keep > kp with a margin for the fp16 rounding error (lemon_rerank certifies the result either way).

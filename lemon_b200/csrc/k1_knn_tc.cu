@@ -767,7 +767,7 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const char* dbg = getenv("LEMON_TC_DEBUG");
   p.debug = dbg ? atoi(dbg) : 0;
   const char* e1 = getenv("LEMON_TC_CERT");   p.cert = e1 ? atoi(e1) : keep;     // experiments
-  if (p.cert < 8 || p.cert > kKeep) p.cert = keep;
+  if (p.cert < 16 || p.cert > kKeep) p.cert = keep;
   const char* e3 = getenv("LEMON_TC_BOOT");   p.boot_tiles = e3 ? atoi(e3) : kBootTiles;
   if (p.boot_tiles != 0 && p.boot_tiles != 8 && p.boot_tiles != 16) p.boot_tiles = kBootTiles;
 
@@ -804,7 +804,7 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
-      nseg < 1 || nseg > 64 || keep < 0 || (keep > 0 && keep < 8) || keep > kKeep || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
+      nseg < 1 || nseg > 64 || keep < 0 || (keep > 0 && keep < 16) || keep > kKeep || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
       (uintptr_t(cand_keys) & (kListCap * 8 - 1)))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 8 KB-aligned cand_keys)", LEMON_MAX_D_TC);
   if (nq == 0) return LEMON_OK;

@@ -24,6 +24,41 @@ def test_library_exports_every_declared_symbol():
     assert lib.lemon_version() >= 100
 
 
+def test_ctypes_signatures_match_the_header():
+    """The ctypes table mirrors include/lemon_b200.h prototype by prototype: same number of parameters, and the same
+    kind (pointer / 64-bit integer / 32-bit integer / floating point) in every position -- a drifted binding would
+    pass garbage to the kernels without any error."""
+    import ctypes as C
+    from lemon_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "lemon_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b[\w\s\*]+?\b(lemon_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S)
+    assert len(protos) == len(_lib.SIGNATURES)
+
+    def kind_c(decl: str) -> str:
+        decl = " ".join(decl.split())
+        if "*" in decl:
+            return "ptr"
+        if decl.startswith(("int64_t", "long long")):
+            return "i64"
+        if decl.startswith(("float", "double")):
+            return decl.split()[0]
+        assert decl.startswith("int"), decl
+        return "i32"
+
+    def kind_py(t) -> str:
+        if t in (C.c_void_p, C.c_char_p) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return "ptr"
+        return {C.c_int64: "i64", C.c_int: "i32", C.c_float: "float", C.c_double: "double"}[t]
+
+    for name, params in protos:
+        params = [p for p in params.split(",") if p.strip() and p.strip() != "void"]
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for i, (pc, pt) in enumerate(zip(params, argtypes)):
+            assert kind_c(pc) == kind_py(pt), (name, i, pc.strip(), pt)
+
+
 def test_sass_has_blackwell_tensor_and_tma_ops():
     import subprocess
     from lemon_b200 import LIB_PATH

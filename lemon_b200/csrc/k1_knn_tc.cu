@@ -15,7 +15,7 @@
 //                             a counting ladder (no sorting or compaction during the scan), are shared between
 //                             the groups and bootstrapped from group maxima.
 // Work item = (query row tile, DB segment); items are dealt round-robin so all CTAs walk the DB
-// in the same order and DB tiles are served from L2.  The union / top-64 selection over a row's lists
+// in the same order and DB tiles are served from L2.  The selection over the union of a row's lists
 // is done by the re-rank kernel (k2_rerank.cu).
 #include <cuda.h>
 #include <cstdlib>
@@ -38,7 +38,7 @@ struct TcParams {
   int64_t seg_len;      // columns per segment (multiple of BN)
   int nstage;
   int64_t n_items;      // row_tiles * nseg
-  uint64_t* cand_keys;  // [nq_pad][nseg][2][kCap]: the streaming key buffers ARE the output
+  uint64_t* cand_keys;  // [nq_pad][nseg][2][kListCap]: the streaming key buffers ARE the output
   int32_t* cand_cnt;    // [nq_pad][nseg][2]
   float* cand_theta;    // [nq_pad][nseg][2]: every column not in the list has approximate value <= theta
   int cert;             // ladder: exceedance count that certifies a level (`keep` of the C ABI)
@@ -550,7 +550,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
     }
   } else if (warp >= 4) {
-    // =============================== epilogue: streaming top-64 ===============================
+    // =============================== epilogue: streaming top-k ===============================
     // Two groups of 4 warps; group g scans columns [g*BN/2, (g+1)*BN/2) of every accumulator tile.  (Groups that
     // alternate whole tiles cannot scan while their buffer is being refilled: the step time was T_mma + T_scan
     // per two tiles; with split tiles it is max(T_mma, T_scan/2 + pruning) per tile.)  Both groups track the
@@ -575,7 +575,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       int cnt = 0;
       Ladder ld;
       ladder_off(ld);
-      // this item's key buffers live in the output array: row-major [row][seg][group][kCap]
+      // this item's key buffers live in the output array: row-major [row][seg][group][kListCap]
       uint64_t* warp_keys = p.cand_keys + ((rt * (kBM * CG) + cta_rank * kBM + quad * 32) * p.nseg + seg) * (kEpiGroups * kListCap) +
                             size_t(grp) * kListCap;
       uint64_t* my_keys = warp_keys + size_t(lane) * row_stride;
@@ -684,7 +684,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
       }
       // ---- item done: the row's key buffer already sits in the output; publish its length and threshold.
-      // (The exact top-64 selection over the union of the lists happens in the re-rank kernel, where thousands
+      // (The exact top-kp selection over the union of the lists happens in the re-rank kernel, where thousands
       // of warps hide its latency; here it would sit on the critical path of one persistent warp.)
       {
         const size_t li = (size_t(row) * p.nseg + seg) * kEpiGroups + grp;

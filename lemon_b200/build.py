@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("LEMON_BUILD_DEFS", "").split()      # e.g. -DLEMON_TC_PROFILE (in-kernel clock counters of K1)
     objs = []
     procs = []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)

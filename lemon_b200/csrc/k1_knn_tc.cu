@@ -19,6 +19,12 @@
 // is done by the re-rank kernel (k2_rerank.cu).
 #include <cuda.h>
 #include <cstdlib>
+#ifdef LEMON_TC_PROFILE
+#include <cstdio>   // in-kernel clock counters (build with LEMON_BUILD_DEFS=-DLEMON_TC_PROFILE; prints from CTA 0)
+#define LEMON_PROF(x) x
+#else
+#define LEMON_PROF(x)
+#endif
 
 #include "lemon_common.cuh"
 
@@ -510,6 +516,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     if (lane == 0 && cta_rank == 0) {
       constexpr uint32_t idesc = (1u << 4) | (uint32_t(BN >> 3) << 17) | (uint32_t((kBM * CG) >> 4) << 24);
       int stage = 0; uint32_t phase = 0; uint32_t it = 0; uint32_t tc = 0;
+      LEMON_PROF(long long pf_empty = 0; long long pf_full = 0; const long long pf_t0 = clock64();)
       for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
         const int64_t seg = item % p.nseg;
         const int64_t col0 = seg * p.seg_len;
@@ -521,8 +528,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);
         for (int64_t i = 0; i < nsteps; ++i, ++tc) {
           const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
+          LEMON_PROF(const long long pf_a = clock64();)
           mbar_wait(tmem_empty + 8 * buf, (use & 1) ^ 1);
           tc_fence_after();
+          LEMON_PROF(pf_empty += clock64() - pf_a;)
           const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kc = 0; kc < p.kchunks; ++kc) {
             uint32_t a_addr = a_smem + kc * kAChunkBytes;
@@ -533,8 +542,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
               a_addr = b_smem + stage * kStageBytes;
               if (++stage == p.nstage) { stage = 0; phase ^= 1; }
             }
+            LEMON_PROF(const long long pf_b = clock64();)
             mbar_wait(full_bar(stage), phase);
             tc_fence_after();
+            LEMON_PROF(pf_full += clock64() - pf_b;)
             const uint64_t adesc = make_smem_desc(a_addr);
             const uint64_t bdesc = make_smem_desc(b_smem + stage * kStageBytes);
 #pragma unroll
@@ -548,6 +559,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         }
         umma_commit<CG>(a_empty);                    // query tile drained (both CTAs)
       }
+      LEMON_PROF(if (blockIdx.x == 0) printf("K1 MMA issuer: total %lld cycles, waiting for a free accumulator %lld, for a full stage %lld, tiles %u\n",
+                                             clock64() - pf_t0, pf_empty, pf_full, tc);)
     }
   } else if (warp >= 4) {
     // =============================== epilogue: streaming top-k ===============================
@@ -564,6 +577,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
     const size_t row_stride = size_t(p.nseg) * kEpiGroups * kListCap;     // keys between consecutive query rows
     const uint32_t tempty0 = (CG == 2) ? mapa_rank0(tmem_empty) : tmem_empty;
     uint32_t tc = 0, it = 0;
+    LEMON_PROF(long long pf_wait = 0; long long pf_scan = 0; long long pf_max = 0; const long long pf_t0 = clock64();)
     for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
       const int64_t rt = item / p.nseg, seg = item % p.nseg;
       const int64_t col0 = seg * p.seg_len;
@@ -587,8 +601,10 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       for (int64_t i = 0; i < nsteps; ++i, ++tc) {
         const int64_t t = i < ntiles ? i : i - ntiles;
         const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
+        LEMON_PROF(const long long pf_a = clock64();)
         mbar_wait(tmem_full + 8 * buf, use & 1);
         tc_fence_after();
+        LEMON_PROF(const long long pf_b = clock64(); pf_wait += pf_b - pf_a;)
         if (i < nboot && bcount >= 0) {
           // ---- bootstrap tile: record the 8-column group maxima only (no appends, no prunes)
           const uint32_t taddr_b = tmem_base + tmem_lane + buf * BN + grp * kGrpCols;
@@ -674,6 +690,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (__any_sync(kFull, cnt > kListCap - 32)) prune_full_rows(warp_keys, row_stride, cnt, theta, ld, p.cert, lane);   // must not overflow
           }
         }
+        LEMON_PROF({ const long long pf_c = clock64() - pf_b; pf_scan += pf_c; if (pf_c > pf_max) pf_max = pf_c; })
         // publish this row's threshold and hand the accumulator buffer back to the MMA warp
         th_sh[grp * kBM + row_local] = tag | __float_as_uint(theta);
         tc_fence_before();
@@ -693,6 +710,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       }
       __syncwarp();
     }
+    LEMON_PROF(if (lane == 0 && blockIdx.x == 0) printf("K1 epilogue warp %d: total %lld cycles, waiting for an accumulator %lld, scanning %lld (longest tile %lld), tiles %u\n",
+                                                       warp, clock64() - pf_t0, pf_wait, pf_scan, pf_max, tc);)
     }
   }
 

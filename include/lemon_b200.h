@@ -57,16 +57,17 @@ int lemon_ctx_destroy(lemon_ctx* ctx);
 const char* lemon_last_error(lemon_ctx* ctx);
 
 /* Row-wise L2 normalisation + 16-bit operand copy (K0).
- *   in        [n, d]  fp32
+ *   in        [n, d]  fp32, rows in_stride floats apart (0 = d: contiguous).  A strided input lets the caller
+ *                     normalise a column block of a wider matrix (the all-gathered [text | label] shard rows)
  *   out_f32   [n, d]  fp32, x / max(||x||, 1e-12) when do_normalize, else a copy (may alias `in`; may be NULL)
  *   out_f16   [n, d16] fp16, the (normalised) row rounded to nearest, zero padded to d16 (multiple of 64; may be NULL)
  *   row_stats [n, 4]  fp32 per row: {||x||, ||fp16(x)||, ||x - fp16(x)||, ||x||^2} of the OUTPUT row (may be NULL)
- *   stats_max [4]     fp32, running maxima over rows of {||x||, ||fp16(x)||, ||x - fp16(x)||, | ||x||^2 - 1 |};
- *                     caller zero-initialises (may be NULL)
+ *   stats_max [4]     fp32, maxima over the n rows of {||x||, ||fp16(x)||, ||x - fp16(x)||, | ||x||^2 - 1 |}
+ *                     (zeroed by the call, on the stream; may be NULL)
  */
 int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* out_f16,
                          float* row_stats, float* stats_max, int64_t n, int d, int d16,
-                         int do_normalize, void* stream);
+                         int64_t in_stride, int do_normalize, void* stream);
 
 /* out[i] = 1 - <a_i, b_i> (metric IP / cosine)  or  sum (a_i - b_i)^2 (metric L2). run_lemon.py:169,173,250-253 */
 int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* out,
@@ -100,13 +101,15 @@ int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int6
  *   that provably cannot be in the exact top-kp, gathers the rest and evaluates them exactly in fp32.
  *   q_row_stats [nq,4], db_stats_max [4]: outputs of lemon_normalize_cast for the query rows and the DB.
  *   They give the rigorous per-row bound on |fp16 tensor-core inner product - exact|:
- *     eps_row = ||q - q16|| * max||b16|| + ||q|| * max||b - b16|| + acc_eps
- *   (Cauchy-Schwarz on the two rounding-error vectors; acc_eps covers fp32 accumulation).  NULL = eps 0.
+ *     eps_row = ||q - q16|| * max||b16|| + ||q|| * max||b - b16|| + acc_eps * max(||q||,||q16||) * max(||b||,||b16||)
+ *   (Cauchy-Schwarz on the two rounding-error vectors; acc_eps is the RELATIVE bound on the fp32 accumulation of
+ *   the tensor-core product plus that of the fp32 re-evaluation: d16 * 2^-23 + (d/32 + 6) * 2^-24, i.e. the
+ *   gamma_n * sum|q_i b_i| bound with truncating adds).  NULL = eps 0.
  *   Metric L2 ranks by -||q-b||^2 = 2<q,b> - ||q||^2 - ||b||^2; the bound then uses ||q||^2 from
  *   q_row_stats and min||b||^2 >= 1 - db_stats_max[3].
  *   top_val / top_idx [nq, kp]: exact top list.  A row is certified when its kp-th exact value beats every
  *   non-candidate's bound (max over lists of cand_theta, + eps_row); otherwise its row id is appended to
- *   uncert_rows[0 .. *n_uncert) (caller zeroes *n_uncert; room for nq ids).
+ *   uncert_rows[0 .. *n_uncert) (*n_uncert is zeroed by the call, on the stream; room for nq ids).
  */
 int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const uint64_t* cand_keys,
                  const int32_t* cand_cnt, const float* cand_theta, const float* q_row_stats,
@@ -134,7 +137,8 @@ int lemon_knn_exact(lemon_ctx* ctx, const float* q, const float* db, const int32
  *   hp[6] = {beta, gamma, tau_1_n, tau_2_n, tau_1_m, tau_2_m}: HOST pointer read at call time, or NULL
  *   (then sn/sm/score are not written)
  *   outputs (any may be NULL): d1 [nq]; Dn,dists_n,dists_tr_n,Dm,dists_m,dists_tr_m [nq,k] fp32;
- *   In, Im [nq,k] int64;  sn, sm, score [nq] float64.
+ *   In, Im [nq,k] int64 (index_bits = 64, what faiss returns) or int32 (index_bits = 32: half the bytes for
+ *   callers that copy the records to the host);  sn, sm, score [nq] float64.
  */
 int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* xdb, const float* ydb,
                 const float* dists_tr, const float* topn_val, const int32_t* topn_idx,
@@ -142,8 +146,8 @@ int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* x
                 const int32_t* label_q, const int32_t* label_db, const float* class_emb,
                 const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                 int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
-                float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, int64_t* In,
-                int64_t* Im, double* sn, double* sm, double* score, void* stream);
+                float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, void* In,
+                void* Im, int index_bits, double* sn, double* sm, double* score, void* stream);
 
 /* Score combination only (lib/metrics/utils.py:63-77) on stacked [n,k] fp32 columns. */
 int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_n, const float* dists_n,
@@ -152,17 +156,40 @@ int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_
                          double* sm, double* score, void* stream);
 
 /* Exact-duplicate DB rows are searched once (classification datasets: C distinct text embeddings; caption noise
- * duplicates captions).  lemon_hash_rows: 63-bit hash of every row's bit pattern (the caller sorts/groups);
- * lemon_rows_equal: sets flag[0] |= 1 if a row differs bit-wise from rep_of_row[row] (hash collision check);
+ * duplicates captions: run_lemon.py:117-119,140-143, lib/datasets/noise_captioning.py:44-53).
+ * lemon_dedup_build groups the bit-identical rows of x [n,d] entirely on the device (hash -> radix sort -> run
+ * scan -> bit-wise verification -> renumbering), without a host round trip:
+ *   workspace   lemon_dedup_workspace_bytes(n) bytes, 256 B aligned (caller-owned scratch)
+ *   counters[2] {n_unique, collision}: collision != 0 means two different rows shared a 63-bit hash; the
+ *               outputs are then unusable and the caller must not de-duplicate
+ *   rep_rows [n]   first n_unique entries: lowest row index of each group, ascending (group u = u-th unique row)
+ *   offsets [n+1]  first n_unique+1 entries: group u owns members[offsets[u] .. offsets[u+1])
+ *   members [n]    row indices grouped by unique row, ascending inside a group
+ * lemon_gather_rows: dst[r] = src[idx[r]] for r < min(*n_idx, max_idx) (n_idx device pointer or NULL = max_idx);
+ *   rows of row_bytes (multiple of 16) bytes.  Builds the unique-row operands from rep_rows.
  * lemon_expand_groups: turns top lists over the unique rows (uval/uidx [nq,kp]) into top lists over the original
- * rows: group u owns members[offsets[u] .. offsets[u+1]) (ascending DB index); entries keep the group's value.
+ *   rows; entries keep the group's value; members of consecutive unique rows with EQUAL values are merged by
+ *   ascending row index (the documented total order).
+ * lemon_hash_rows: the 63-bit row hash alone (diagnostics / tests).
  */
+int64_t lemon_dedup_workspace_bytes(int64_t n);
+int lemon_dedup_build(lemon_ctx* ctx, const float* x, int64_t n, int d, void* workspace, int32_t* rep_rows,
+                      int32_t* members, int64_t* offsets, int32_t* counters, void* stream);
+int lemon_gather_rows(lemon_ctx* ctx, const void* src, const int32_t* idx, const int32_t* n_idx, int64_t max_idx,
+                      int64_t row_bytes, void* dst, void* stream);
 int lemon_hash_rows(lemon_ctx* ctx, const float* x, int64_t n, int d, int64_t* out, void* stream);
-int lemon_rows_equal(lemon_ctx* ctx, const float* x, const int64_t* rep_of_row, int64_t n, int d,
-                     int32_t* flag, void* stream);
 int lemon_expand_groups(lemon_ctx* ctx, const float* uval, const int32_t* uidx, const int64_t* offsets,
                         const int32_t* members, int64_t nq, int kp, int metric, float* top_val,
                         int32_t* top_idx, void* stream);
+
+/* CC3M filtering consumer of the scores (train_clip_from_scratch.py:110-113: sort ascending by score, keep the first
+ * cc3m_filtering_n rows).  out_idx [n_keep] int64 = row ids of the n_keep LOWEST scores in ascending score order
+ * (ties: lower row id first; pandas' default quicksort leaves tie order unspecified), out_score [n_keep] their
+ * scores (may be NULL).  workspace: lemon_keep_lowest_workspace_bytes(n) bytes, 256 B aligned.  NaN scores sort last.
+ */
+int64_t lemon_keep_lowest_workspace_bytes(int64_t n);
+int lemon_keep_lowest(lemon_ctx* ctx, const double* score, int64_t n, int64_t n_keep, void* workspace,
+                      int64_t* out_idx, double* out_score, void* stream);
 
 /* Hyper-parameter grid stage (lib/metrics/utils.py:117-121,167-186,286-296): for each of n_points grid points
  *   score_i = d1[i] + beta[g] * sn[tidx[g], i] + gamma[g] * sm[tidx[g], i]      (all float64, utils.py:77)

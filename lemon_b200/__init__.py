@@ -9,10 +9,23 @@ Public surface (mirrors the reference's seams):
 """
 from . import _lib
 from ._lib import LemonError, LIB_PATH
-from .scoring import LemonScorer, score_pairs, get_scorer, plan_segments, plan_tail, HP_KEYS
+from .scoring import (LemonScorer, score_pairs, get_scorer, plan_segments, plan_tail, HP_KEYS, subsample_db,
+                      query_in_db_from_indices)
 
 __all__ = ["LemonScorer", "score_pairs", "get_scorer", "plan_segments", "LemonError", "LIB_PATH", "HP_KEYS",
-           "install_faiss_shim", "patch_reference_metrics"]
+           "install_faiss_shim", "patch_reference_metrics", "subsample_db", "query_in_db_from_indices",
+           "filter_lowest_scores"]
+
+
+def filter_lowest_scores(score, n_keep: int, idx=None, device=None):
+    """train_clip_from_scratch.py:110-113 (`score_df.sort_values(by='score').iloc[:cc3m_filtering_n]['idx'].values`) on
+    the device: the `idx` values (default: row numbers) of the n_keep lowest-scored pairs in ascending score order."""
+    import torch
+    order, _ = get_scorer(device).keep_lowest(score, n_keep)
+    if idx is None:
+        return order
+    idx_t = torch.as_tensor(idx).to(order.device)
+    return idx_t[order]
 
 
 def install_faiss_shim():

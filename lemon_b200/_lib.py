@@ -25,7 +25,7 @@ SIGNATURES = {
     "lemon_last_error": (C.c_char_p, [C.c_void_p]),
     "lemon_launch_count": (C.c_int64, [C.c_void_p]),
     "lemon_normalize_cast": (C.c_int, [C.c_void_p, c_f32p, c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_int64,
-                                       C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                       C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]),
     "lemon_rowwise_dist": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
     "lemon_knn_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                        C.c_int, C.c_int, c_i64p, c_i32p, c_f32p, C.c_void_p]),
@@ -36,10 +36,15 @@ SIGNATURES = {
                                   C.c_int, C.c_int, C.c_int, c_f32p, c_i32p, C.c_void_p]),
     "lemon_score": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p,
                               c_i64p, c_i32p, c_i32p, c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
-                              C.c_int, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i64p,
-                              c_i64p, c_f64p, c_f64p, c_f64p, C.c_void_p]),
+                              C.c_int, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p,
+                              C.c_void_p, C.c_int, c_f64p, c_f64p, c_f64p, C.c_void_p]),
     "lemon_hash_rows": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int, c_i64p, C.c_void_p]),
-    "lemon_rows_equal": (C.c_int, [C.c_void_p, c_f32p, c_i64p, C.c_int64, C.c_int, c_i32p, C.c_void_p]),
+    "lemon_dedup_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "lemon_dedup_build": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int, C.c_void_p, c_i32p, c_i32p, c_i64p, c_i32p,
+                                    C.c_void_p]),
+    "lemon_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, c_i32p, c_i32p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
+    "lemon_keep_lowest_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "lemon_keep_lowest": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, C.c_int64, C.c_void_p, c_i64p, c_f64p, C.c_void_p]),
     "lemon_expand_groups": (C.c_int, [C.c_void_p, c_f32p, c_i32p, c_i64p, c_i32p, C.c_int64, C.c_int, C.c_int, c_f32p,
                                       c_i32p, C.c_void_p]),
     "lemon_f1_grid": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, C.c_void_p, C.c_int64, c_f64p, c_f64p, c_i32p,

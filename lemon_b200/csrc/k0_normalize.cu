@@ -14,12 +14,12 @@ __device__ __forceinline__ void atomic_max_pos(float* addr, float v) {
 __global__ void __launch_bounds__(256)
 normalize_cast_kernel(const float* __restrict__ in, float* __restrict__ out_f32, __half* __restrict__ out_f16,
                       float* __restrict__ row_stats, float* __restrict__ stats_max, int64_t n, int d, int d16,
-                      int do_normalize) {
+                      int64_t in_stride, int do_normalize) {
   const int lane = threadIdx.x & 31;
   const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
   float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
   for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
-    const float* x = in + row * d;
+    const float* x = in + row * in_stride;
     float ss = 0.f;
     for (int c = lane; c < d; c += 32) { float v = x[c]; ss = fmaf(v, v, ss); }
     ss = warp_sum(ss);
@@ -66,18 +66,22 @@ rowwise_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 
 extern "C" int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* out_f16,
                                     float* row_stats, float* stats_max, int64_t n, int d, int d16,
-                                    int do_normalize, void* stream) {
+                                    int64_t in_stride, int do_normalize, void* stream) {
   if (!ctx) return LEMON_ERR_INVALID;
   if (!in || n < 0 || d <= 0) return lemon_set_error(ctx, LEMON_ERR_INVALID, "normalize_cast: bad args");
   if (out_f16 && (d16 < d || d16 % 64)) return lemon_set_error(ctx, LEMON_ERR_INVALID, "normalize_cast: d16 must be a multiple of 64 and >= d");
+  if (in_stride == 0) in_stride = d;
+  if (in_stride < d || (in_stride != d && out_f32 == in))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "normalize_cast: in_stride must be >= d (and out_f32 must not alias a strided input)");
   if (!out_f16) d16 = d;
   if (n == 0) return LEMON_OK;
+  if (stats_max) LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(stats_max, 0, 4 * sizeof(float), (cudaStream_t)stream));
   const int threads = 256;
   int64_t blocks = (n + 7) / 8;
   const int64_t cap = int64_t(ctx->num_sms) * 16;
   if (blocks > cap) blocks = cap;
   lemon::normalize_cast_kernel<<<unsigned(blocks), threads, 0, (cudaStream_t)stream>>>(
-      in, out_f32, (__half*)out_f16, row_stats, stats_max, n, d, d16, do_normalize);
+      in, out_f32, (__half*)out_f16, row_stats, stats_max, n, d, d16, in_stride, do_normalize);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());
   return LEMON_OK;

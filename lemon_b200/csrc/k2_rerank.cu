@@ -47,7 +47,10 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
     float eps = 0.f, qsq = 1.f, dbdev = 0.f;
     if (q_row_stats) {
       const float4 st = reinterpret_cast<const float4*>(q_row_stats)[row];   // {||q||, ||q16||, ||q-q16||, ||q||^2}
-      eps = st.z * db_stats_max[1] + st.x * db_stats_max[2] + acc_eps;
+      // rounding of the two operands (Cauchy-Schwarz) + accumulation, the latter relative to the norms (acc_eps is
+      // a coefficient: d-dependent, see lemon_b200.h) so that un-normalised rows stay rigorously bounded
+      eps = st.z * db_stats_max[1] + st.x * db_stats_max[2] +
+            acc_eps * fmaxf(st.x, st.y) * fmaxf(db_stats_max[0], db_stats_max[1]);
       qsq = st.w;
       dbdev = db_stats_max[3];
     }
@@ -192,6 +195,7 @@ extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, con
   if (!q || !db || !cand_keys || !cand_cnt || !cand_theta || !top_val || !top_idx || !uncert_rows || !n_uncert || nq < 0 ||
       d <= 0 || kp < 1 || kp > LEMON_MAX_KP || nlist < 1 || (q_row_stats && !db_stats_max))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "rerank: bad args");
+  LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(n_uncert, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kRrWarps - 1) / kRrWarps;
   const int64_t cap = int64_t(ctx->num_sms) * 8;

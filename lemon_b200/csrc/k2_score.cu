@@ -20,7 +20,7 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
              const float* __restrict__ class_emb, const int32_t* __restrict__ noisy_label, int n_class, int64_t nq,
              int64_t m, int d, int k, int kp, ScoreHp hp, float* __restrict__ d1, float* __restrict__ Dn, float* __restrict__ dists_n,
              float* __restrict__ dists_tr_n, float* __restrict__ Dm, float* __restrict__ dists_m,
-             float* __restrict__ dists_tr_m, int64_t* __restrict__ In, int64_t* __restrict__ Im,
+             float* __restrict__ dists_tr_m, int64_t* __restrict__ In, int64_t* __restrict__ Im, int idx32,
              double* __restrict__ sn, double* __restrict__ sm, double* __restrict__ score) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warps = int64_t(gridDim.x) * kScWarps;
@@ -110,10 +110,10 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
           const int64_t o = row * k + j;
           if (side == 0) {
             if (Dn) Dn[o] = rD[s]; if (dists_n) dists_n[o] = rdist[s]; if (dists_tr_n) dists_tr_n[o] = rdtr[s];
-            if (In) In[o] = ridx[s];
+            if (In) { if (idx32) reinterpret_cast<int32_t*>(In)[o] = ridx[s]; else In[o] = ridx[s]; }
           } else {
             if (Dm) Dm[o] = rD[s]; if (dists_m) dists_m[o] = rdist[s]; if (dists_tr_m) dists_tr_m[o] = rdtr[s];
-            if (Im) Im[o] = ridx[s];
+            if (Im) { if (idx32) reinterpret_cast<int32_t*>(Im)[o] = ridx[s]; else Im[o] = ridx[s]; }
           }
           if (hp.has) {   // utils.py:71-75
             const double t1 = side == 0 ? hp.t1n : hp.t1m, t2 = side == 0 ? hp.t2n : hp.t2m;
@@ -178,15 +178,15 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
                            const int32_t* label_q, const int32_t* label_db, const float* class_emb,
                            const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                            int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
-                           float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, int64_t* In,
-                           int64_t* Im, double* sn, double* sm, double* score, void* stream) {
+                           float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, void* In,
+                           void* Im, int index_bits, double* sn, double* sm, double* score, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!xq || !yq || !xdb || !ydb || !dists_tr || !topn_val || !topn_idx || !topm_val || !topm_idx || nq < 0 || d <= 0 ||
       k < 1 || k > 64 || (kp != k && kp != k + 1) || (query_in_db && kp != k + 1) || (!query_in_db && kp != k) ||
       ((label_q == nullptr) != (label_db == nullptr)) || ((class_emb == nullptr) != (noisy_label == nullptr)) ||
-      (class_emb && n_class < 1))
-    return lemon_set_error(ctx, LEMON_ERR_INVALID, "score: bad args (kp must be k+1 with query_in_db, k without)");
+      (class_emb && n_class < 1) || (index_bits != 64 && index_bits != 32))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "score: bad args (kp must be k+1 with query_in_db, k without; index_bits 32 or 64)");
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kScWarps - 1) / kScWarps;
   const int64_t cap = int64_t(ctx->num_sms) * 6;   // 3 resident blocks per SM (<= 80 registers), two waves
@@ -195,11 +195,11 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
   if (metric == LEMON_METRIC_IP)
     score_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
         xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
-        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sn, sm, score);
   else
     score_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
         xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
-        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, In, Im, sn, sm, score);
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sn, sm, score);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());
   return LEMON_OK;

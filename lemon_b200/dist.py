@@ -1,15 +1,20 @@
 """Row-sharded multi-GPU driver: one process per GPU, every rank owns a
 contiguous block of pairs (its queries AND its slice of the database), the database is
 replicated with one all-gather per modality over NCCL/NVLink, and there is no other
-collective — every output row is produced by the rank that owns it.
+collective — every output row is produced by the rank that owns it.  (With the discrete text
+metric the int32 label ids travel as four extra columns of the TEXT all-gather; K0 reads the
+embedding columns of the gathered matrix in place through its row stride.)
 
-The collective plumbing is backend-agnostic (tested on CPU with gloo, world_size 2); the
-scoring itself needs the CUDA library.
+The collective plumbing is backend-agnostic (tested on CPU with gloo, world_size 2, with a
+scorer that implements the same staged interface on the CPU oracle); the scoring itself needs
+the CUDA library.
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+LABEL_COLS = 4      # label ids ride in 4 extra fp32 columns (keeps rows 16 B aligned); column 0 holds the int32 bits
 
 
 def shard_bounds(n: int, world: int, rank: int) -> tuple[int, int, int]:
@@ -37,18 +42,42 @@ def allgather_rows(local: torch.Tensor, n_total: int, group=None) -> torch.Tenso
 
 
 _copy_streams: dict = {}
+_qid_cache: dict = {}
+
+
+def _global_row_ids(scorer, r0: int, r1: int) -> torch.Tensor:
+    """query_in_db of this rank's rows (their own global row ids), built once per (device, row range)."""
+    key = (str(scorer.device), r0, r1)
+    t = _qid_cache.get(key)
+    if t is None:
+        _qid_cache.clear()
+        t = _qid_cache[key] = torch.arange(r0, r1, dtype=torch.int64, device=scorer.device)
+    return t
+
+
+def _side_stream(dev, which: str):
+    key = (dev.index, which)
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(dev)
+    return _copy_streams[key]
 
 
 def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type: str = "cosine",
                         hparams=None, normalize: bool = True, return_records: bool = True, scorer=None,
-                        group=None, text_label_ids_local=None) -> dict:
+                        group=None, text_label_ids_local=None, host_out: dict | None = None,
+                        index_dtype=torch.int64, d2h_parts: int = 4) -> dict:
     """Every rank passes its padded shard [per, d] of both modalities.  The DB is all pairs (train-split
     self-exclusion on, query_in_db = own global row ids).  Returns this rank's rows of every output (see
     lemon_b200.score_pairs) plus 'rows' = (r0, r1).
 
     Shards may be device tensors or (pinned) HOST tensors.  With host tensors both host->device copies are
     issued up front on a copy stream and the whole image side (all-gather, K0, K1, K2a) runs while the text
-    shard is still in flight; the text side starts when its copy has landed."""
+    shard is still in flight; the text side starts when its copy has landed.
+
+    host_out: dict of pinned host tensors (one per output column, at least r1-r0 rows; missing ones are created
+    and added).  The records are then produced in `d2h_parts` row parts and each part's device->host copy runs on
+    a copy stream while the next part is being computed; the call returns host tensors once all copies have
+    landed.  index_dtype=torch.int32 halves the bytes of I_n / I_m (faiss's int64 is the default)."""
     from .scoring import METRIC, _slice_prepared, _to_dev
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -57,65 +86,100 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     if scorer is None:
         from .scoring import get_scorer
         scorer = get_scorer(img_local.device.index if img_local.is_cuda else None)
-    if not hasattr(scorer, "prepare_db"):        # stand-in scorers (CPU tests): plain sequential path
-        img_db = allgather_rows(img_local, n_total, group)
-        txt_db = allgather_rows(txt_local, n_total, group)
-        lab_db = None
-        if text_label_ids_local is not None:
-            lab_db = allgather_rows(text_label_ids_local.view(-1, 1), n_total, group).view(-1)
-        scorer.set_database(img_db, txt_db, dist_type, normalize, lab_db)
-        qid = torch.arange(r0, r1, dtype=torch.int64, device=img_local.device)
-        out = scorer.score(None, None, k=k, query_in_db=qid, hparams=hparams, return_records=return_records,
-                           query_rows=(r0, r1), text_label_ids_q=lab_db[r0:r1] if lab_db is not None else None)
-        out["rows"] = (r0, r1)
-        return out
-
     dev = scorer.device
-    main = torch.cuda.current_stream(dev)
+    on_gpu = dev.type == "cuda"
+    d = img_local.shape[1]
+    with_labels = text_label_ids_local is not None
+    main = torch.cuda.current_stream(dev) if on_gpu else None
     e_txt = None
-    if not img_local.is_cuda:
-        cs = _copy_streams.get(dev.index)
-        if cs is None:
-            cs = _copy_streams[dev.index] = torch.cuda.Stream(dev)
+
+    def stage_text(t):
+        """The text shard as it is all-gathered: [per, d], or [per, d + LABEL_COLS] with the label ids."""
+        if not with_labels:
+            return t.to(dev, non_blocking=True)
+        wide = torch.zeros((per, d + LABEL_COLS), dtype=torch.float32, device=dev)
+        wide[:, :d].copy_(t, non_blocking=True)
+        lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
+        wide[:, d].copy_(lab.view(torch.float32))
+        return wide
+
+    if on_gpu and not img_local.is_cuda:
+        cs = _side_stream(dev, "h2d")
         cs.wait_stream(main)
         with torch.cuda.stream(cs):
             img_local = img_local.to(dev, non_blocking=True)
             e_img = torch.cuda.Event()
             e_img.record(cs)
-            txt_local = txt_local.to(dev, non_blocking=True)
+            txt_wide = stage_text(txt_local)
             e_txt = torch.cuda.Event()
             e_txt.record(cs)
         img_local.record_stream(main)
-        txt_local.record_stream(main)
+        txt_wide.record_stream(main)
         main.wait_event(e_img)
+    else:
+        txt_wide = stage_text(txt_local)
     metric = METRIC[dist_type]
     kp = k + 1
     # ---- image side (run_lemon.py:164,168/172,176,235) while the text shard may still be copying
-    xdb = scorer.prepare_db(allgather_rows(img_local, n_total, group), normalize)
-    xq = _slice_prepared(xdb, r0, r1)
-    ydb = None
+    xdb = scorer.prepare_db(allgather_rows(img_local, n_total, group), normalize, defer_dedup=True)
+    ydb = txt_all = None
+
+    def stage_text_db():
+        nonlocal txt_all
+        txt_all = allgather_rows(txt_wide, n_total, group)
+        return scorer.prepare_db(txt_all[:, :d] if with_labels else txt_all, normalize, defer_dedup=True)
+
     if e_txt is None:
-        # device-resident shards: stage the text side too before the long kernels are queued (duplicate
-        # detection reads two scalars back; doing it now keeps the host ahead of the GPU)
-        ydb = scorer.prepare_db(allgather_rows(txt_local, n_total, group), normalize)
+        # device-resident shards: stage the text side too before the long kernels are queued, so that the duplicate
+        # detection of both matrices costs ONE host round trip (it reads their counters back)
+        ydb = stage_text_db()
+    scorer.finish_db(xdb)
+    if ydb is not None:
+        scorer.finish_db(ydb)
+    xq = _slice_prepared(xdb, r0, r1)
     topn = scorer.knn(xq, xdb, kp, metric)
     info_n = scorer.last_info
     # ---- text side
     if ydb is None:
         main.wait_event(e_txt)
-        ydb = scorer.prepare_db(allgather_rows(txt_local, n_total, group), normalize)
+        ydb = scorer.finish_db(stage_text_db())
     yq = _slice_prepared(ydb, r0, r1)
     dtr = scorer.rowwise_dist(ydb.f32, xdb.f32, metric)
     topm = scorer.knn(yq, ydb, kp, metric)
     info_m = scorer.last_info
     lab_db = lab_q = None
-    if text_label_ids_local is not None:
-        lab_local = _to_dev(text_label_ids_local, dev, torch.int32)
-        lab_db = allgather_rows(lab_local.view(-1, 1), n_total, group).view(-1).contiguous()
+    if with_labels:
+        lab_db = txt_all[:, d].contiguous().view(torch.int32)
         lab_q = lab_db[r0:r1]
-    qid = torch.arange(r0, r1, dtype=torch.int64, device=dev)
-    out = scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, k=k, kp=kp, metric=metric, qid=qid, lab_q=lab_q, lab_db=lab_db,
-                      hparams=hparams, return_records=return_records)
+    qid = _global_row_ids(scorer, r0, r1)
+    nq = r1 - r0
+    common = dict(k=k, kp=kp, metric=metric, qid=qid, lab_q=lab_q, lab_db=lab_db, hparams=hparams,
+                  return_records=return_records, index_dtype=index_dtype)
+    if host_out is None or not on_gpu:
+        out = scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, **common)
+    else:
+        # records part by part; the copy stream ships part i to the host while part i+1 is computed
+        out_dev = scorer.alloc_outputs(nq, k, hparams, return_records, index_dtype)
+        ds = _side_stream(dev, "d2h")
+        for name, t in out_dev.items():
+            h = host_out.get(name)
+            if h is None or h.shape[0] < nq or h.dtype != t.dtype or h.shape[1:] != t.shape[1:]:
+                host_out[name] = torch.empty((per,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+        parts = max(1, min(int(d2h_parts), nq))
+        step = -(-nq // parts)
+        for a in range(0, nq, step):
+            b = min(nq, a + step)
+            scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, out=out_dev, rows=(a, b), **common)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ds.wait_event(ev)
+            with torch.cuda.stream(ds):
+                for name, t in out_dev.items():
+                    host_out[name][a:b].copy_(t[a:b], non_blocking=True)
+        for t in out_dev.values():
+            t.record_stream(ds)
+        ds.synchronize()                       # the caller holds the results on the host
+        out = {name: host_out[name][:nq] for name in out_dev}
     scorer.last_info = {"img": info_n, "txt": info_m}
     out["rows"] = (r0, r1)
     return out

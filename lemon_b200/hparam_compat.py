@@ -110,39 +110,40 @@ def grid_search(rec, y, grid: dict, force_zero=(), force_one=()):
 
 def maximize_metric(ref_utils, df, grid, x0s, obj_func, obj_func_args, force_zero=[], force_one=[],
                     scipy_methods=["Powell", "Nelder-Mead"]):
-    """maximize_metric (utils.py:151-196) with the grid stage on the GPU.  The scipy and LBFGS stages stay the
-    reference's own (`ref_utils.maximize_metric_scipy/_torch`, `optim_func`); with patch_reference_hparam_search
-    their objective evaluations run on the GPU as well."""
-    best_x, best_val = None, -1
-    for x in x0s:
-        for method in scipy_methods:
-            temp = ref_utils.maximize_metric_scipy(df, x, obj_func, obj_func_args, method=method,
-                                                   force_zero=force_zero, force_one=force_one)
-            if -temp.fun > best_val:
-                best_val, best_x = -temp.fun, temp.x
-    for x in x0s:
-        cand_x = ref_utils.maximize_metric_torch(df, x, obj_func, obj_func_args, force_zero=force_zero,
-                                                 force_one=force_one)["x"]
-        temp = ref_utils.optim_func(cand_x, df, obj_func, obj_func_args, force_zero=force_zero, force_one=force_one)
-        if -temp > best_val:
-            best_val, best_x = -temp, cand_x
+    """maximize_metric (utils.py:151-196) with the grid stage on the GPU.
+
+    The reference's own function (kept as ``ref_utils._lemon_orig_maximize_metric`` by
+    ``patch_reference_hparam_search``) still runs its scipy and LBFGS stages and the FIRST grid point; all grid
+    points are then evaluated by one ``lemon_f1_grid`` launch and a better one replaces the incumbent under the same
+    strict ``>`` and visiting order as utils.py:167-186.  The GPU grid hard-codes the F1 objective, so it is used
+    only when ``obj_func`` is this module's ``optimize_f1_efficient`` (or the reference's) without extra arguments;
+    any other objective (e.g. ``f1_with_pred_prev_constraint``) runs the reference loop unchanged."""
+    orig = getattr(ref_utils, "_lemon_orig_maximize_metric", None)
+    if orig is None:
+        raise RuntimeError("call patch_reference_hparam_search(ref_utils) first")
+    f1_objs = (optimize_f1_efficient, getattr(ref_utils, "_lemon_orig_optimize_f1_efficient", None))
+    if obj_func not in f1_objs or obj_func_args:
+        return orig(df, grid, x0s, obj_func, obj_func_args, force_zero=force_zero, force_one=force_one,
+                    scipy_methods=scipy_methods)
+    first_point = {name: [vals[0]] for name, vals in grid.items()}
+    best_x, best_val, best_thr = orig(df, first_point, x0s, obj_func, obj_func_args, force_zero=force_zero,
+                                      force_one=force_one, scipy_methods=scipy_methods)
     gx, gval, _, _ = grid_search(df, df["is_mislabel"].values, grid, force_zero, force_one)
     if gval > best_val:
-        best_val, best_x = gval, gx
-    best_x = list(best_x)
-    for c, name in enumerate(HP_KEYS):
-        if name in force_zero:
-            best_x[c] = 0.0
-        if name in force_one:
-            best_x[c] = 1.0
-    score = ref_utils.calc_scores_given_hparams_vectorized(
-        df, ref_utils.unpack_vector(best_x, force_zero=force_zero, force_one=force_one))
-    return best_x, best_val, obj_func(df["is_mislabel"], score, return_thres=True, **obj_func_args)[1]
+        _, eff = grid_points({k: [v] for k, v in zip(HP_KEYS, gx)}, force_zero, force_one)
+        best_x, best_val = list(eff[0]), gval
+        score = ref_utils.calc_scores_given_hparams_vectorized(
+            df, ref_utils.unpack_vector(best_x, force_zero=force_zero, force_one=force_one))
+        best_thr = obj_func(df["is_mislabel"], score, return_thres=True)[1]
+    return best_x, best_val, best_thr
 
 
 def patch_reference_hparam_search(ref_utils):
     """lib.metrics.utils: F1 objective, scoring function and grid stage -> GPU (run_lemon.py:324-394 unchanged)."""
     from . import metrics_compat
+    if not hasattr(ref_utils, "_lemon_orig_maximize_metric"):
+        ref_utils._lemon_orig_maximize_metric = ref_utils.maximize_metric
+        ref_utils._lemon_orig_optimize_f1_efficient = ref_utils.optimize_f1_efficient
     ref_utils.optimize_f1_efficient = optimize_f1_efficient
     ref_utils.calc_scores_given_hparams_vectorized = metrics_compat.calc_scores_given_hparams_vectorized
     ref_utils.maximize_metric = lambda *a, **k: maximize_metric(ref_utils, *a, **k)

@@ -2,7 +2,19 @@
 (lib/metrics/utils.py:47-82): same arguments, same return values, the weighting and reduction run
 in the ``lemon_combine_scores`` kernel.  The [N,k] columns are stacked once per DataFrame and kept
 on the device (the reference re-stacks the object columns on every call, which dominates the
-7056-point hyper-parameter grid, run_lemon.py:332-337)."""
+7056-point hyper-parameter grid, run_lemon.py:332-337).
+
+Two call styles of the reference are kept apart:
+
+* ``torch_arr=False`` (run_lemon.py:406, ``optim_func`` utils.py:117-121, train_clip_from_scratch.py:110):
+  plain numbers in, numpy float64 out -> the CUDA kernel.  The kernel exponentiates and sums in float64 where
+  the reference's numpy path does so in fp32 (utils.py:71-75), so values agree to ~1e-7 relative, not bit for bit.
+* ``torch_arr=True`` (``optim_func_torch`` utils.py:123-127, the LBFGS stage): the hyper-parameters are tensors that
+  require grad and the caller runs ``loss.backward()`` on the result, so the weighting has to stay on the autograd
+  tape.  That stage is outside the scoring hot path; it is evaluated with differentiable torch ops on the cached
+  device columns, operation for operation as utils.py:56-61 (fp32 columns, float64 ``d_1``), and returned as a CPU
+  float64 tensor with its ``grad_fn`` intact.
+"""
 from __future__ import annotations
 
 import weakref
@@ -10,39 +22,76 @@ import weakref
 import numpy as np
 import torch
 
-from .scoring import get_scorer
+from .scoring import HP_KEYS, get_scorer
 
 _COLS = ("D_n", "D_m", "dists_tr_n", "dists_tr_m", "dists_n", "dists_m")
 _cache: dict = {}
 
 
+def _fingerprint(df):
+    """Cheap guard against in-place edits of a cached DataFrame (e.g. ``df['d_1'] = 0.0`` for an ablation, or a
+    rewritten record column): length, the d_1 sum and the identity of every record column's first/last cell."""
+    d1 = np.asarray(df["d_1"].values, dtype=np.float64)
+    cells = []
+    for c in _COLS:
+        v = df[c].values
+        cells.append((id(v[0]), id(v[-1])) if len(v) else ())
+    return (len(df), float(d1.sum()) if len(d1) else 0.0, float(d1[0]) if len(d1) else 0.0, tuple(cells))
+
+
 def _stacked(df):
     key = id(df)
+    fp = _fingerprint(df)
     ent = _cache.get(key)
-    if ent is not None and ent[0]() is df and ent[1] == len(df):
+    if ent is not None and ent[0]() is df and ent[1] == fp:
         return ent[2]
     sc = get_scorer()
     rec = {c: torch.from_numpy(np.stack(df[c].values).astype(np.float32)).to(sc.device) for c in _COLS}
-    rec["d_1"] = torch.from_numpy(np.asarray(df["d_1"].values, dtype=np.float64)).to(sc.device)
+    rec["d_1"] = torch.from_numpy(np.array(df["d_1"].values, dtype=np.float64)).to(sc.device)
     try:
-        _cache[key] = (weakref.ref(df, lambda _r, k=key: _cache.pop(k, None)), len(df), rec)
+        _cache[key] = (weakref.ref(df, lambda _r, k=key: _cache.pop(k, None)), fp, rec)
     except TypeError:
         pass
     return rec
 
 
+def _needs_autograd(hparams) -> bool:
+    return any(torch.is_tensor(hparams[k]) and hparams[k].requires_grad for k in HP_KEYS)
+
+
+def _scores_autograd(rec, hp):
+    """utils.py:56-61 with torch ops (differentiable in the hyper-parameters)."""
+    dev = rec["D_n"].device
+    h = {k: (hp[k].to(dev) if torch.is_tensor(hp[k]) else hp[k]) for k in HP_KEYS}
+    w_n = torch.exp(-h["tau_1_n"] * rec["D_n"]) * torch.exp(-h["tau_2_n"] * rec["dists_tr_n"])
+    w_m = torch.exp(-h["tau_1_m"] * rec["D_m"]) * torch.exp(-h["tau_2_m"] * rec["dists_tr_m"])
+    d_ns = torch.sum(w_n * rec["dists_n"], dim=1) / rec["D_n"].shape[1]
+    d_ms = torch.sum(w_m * rec["dists_m"], dim=1) / rec["D_m"].shape[1]
+    scores = rec["d_1"] + h["beta"] * d_ns + h["gamma"] * d_ms
+    return scores, d_ns, d_ms
+
+
 def calc_scores_given_hparams_vectorized(df, best_hparams, return_dn=False, torch_arr=False):
     rec = _stacked(df)
-    sc = get_scorer()
-    scores, d_ns, d_ms = sc.combine_scores(rec, best_hparams)
-    if torch_arr:
-        scores, d_ns, d_ms = scores.cpu(), d_ns.cpu(), d_ms.cpu()
+    if torch_arr or _needs_autograd(best_hparams):
+        scores, d_ns, d_ms = (t.cpu() for t in _scores_autograd(rec, best_hparams))
+        if not torch_arr:
+            scores, d_ns, d_ms = (t.detach().numpy() for t in (scores, d_ns, d_ms))
     else:
-        scores, d_ns, d_ms = scores.cpu().numpy(), d_ns.cpu().numpy(), d_ms.cpu().numpy()
+        sc = get_scorer()
+        hp = {k: float(best_hparams[k]) for k in HP_KEYS}
+        scores, d_ns, d_ms = (t.cpu().numpy() for t in sc.combine_scores(rec, hp))
     if return_dn:
         return scores, d_ns, d_ms
     return scores
 
 
-def clear_cache():
-    _cache.clear()
+def invalidate(df=None):
+    """Drops the cached device columns of `df` (all DataFrames when None)."""
+    if df is None:
+        _cache.clear()
+    else:
+        _cache.pop(id(df), None)
+
+
+clear_cache = invalidate

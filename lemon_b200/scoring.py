@@ -20,9 +20,17 @@ KPRIME = 64
 LIST_CAP = 1024
 MAX_KP = 64
 MAX_D_TC = 768
-# bound on the fp32 accumulation error of the tensor-core inner product (|q|,|b| <= ~1);
-# validated on the GPU by tests/test_gpu_parity.py::test_tc_error_bound
-ACC_EPS = 3e-5
+
+
+def acc_eps_coef(d16: int, d: int) -> float:
+    """RELATIVE bound (a factor of ||q|| * max||b||) on the accumulation error the re-rank certificate must allow
+    for: the tensor-core inner product adds d16 exact fp16 x fp16 products into an fp32 accumulator (gamma_n bound
+    with truncating adds: d16 * 2^-23 * sum|q_i b_i| <= d16 * 2^-23 * ||q|| ||b||), and the fp32 re-evaluation
+    every kernel reports (warp_pair_value: d/32 sequential fma per lane + a 5-level butterfly) adds
+    (d/32 + 6) * 2^-24.  Both scale with the norms, so un-normalised inputs (faiss_compat, normalize=False) stay
+    rigorously bounded; tests/test_gpu_parity.py::test_tc_error_bound_is_rigorous checks it on the GPU."""
+    return float(d16) * 2.0 ** -23 + (d / 32.0 + 6.0) * 2.0 ** -24
+
 METRIC = {"ip": 0, "cosine": 0, "l2": 1, "euclidean": 1}
 
 
@@ -85,6 +93,38 @@ def decode_candidates(cand_keys: torch.Tensor, cand_cnt: torch.Tensor, n_rows: i
     idx = np.where(valid, idx, -1).reshape(n, -1)
     order = np.lexsort((idx, -vals), axis=1)
     return np.take_along_axis(vals, order, 1), np.take_along_axis(idx, order, 1)
+
+
+def subsample_db(n_train: int, limit: int = 50_000, rng=None) -> np.ndarray:
+    """run_lemon.py:122-127 (`--compr_dataset_size_limit`, default 50 000 at :48): the kNN database is the whole
+    train split, or `limit` rows drawn without replacement (unsorted, global numpy RNG unless `rng` is given)
+    when the split is larger.  Returns ``train_indices_in_compr``: DB row j holds train sample out[j]."""
+    if n_train > limit:
+        rng = np.random if rng is None else rng
+        return rng.choice(np.arange(n_train), limit, replace=False)
+    return np.arange(n_train)
+
+
+def query_in_db_from_indices(n_queries: int, train_indices_in_compr) -> np.ndarray:
+    """The ``query_in_db`` argument of score_pairs for train-split queries 0 .. n_queries-1: the DB row that holds
+    each sample, or -1 when the subsample left it out.  The reference only tests membership
+    (`sample_idx in train_indices_in_compr`, run_lemon.py:258,278, an O(M) scan per sample); one scatter does it
+    for all samples."""
+    idx = np.asarray(train_indices_in_compr.cpu() if torch.is_tensor(train_indices_in_compr) else train_indices_in_compr,
+                     dtype=np.int64).reshape(-1)
+    out = np.full(int(n_queries), -1, dtype=np.int64)
+    ok = (idx >= 0) & (idx < n_queries)
+    out[idx[ok]] = np.nonzero(ok)[0]
+    return out
+
+
+def count_uncertified(info: dict) -> "int | None":
+    """Rows of a kNN call (``LemonScorer.last_info`` of one side) that the re-rank certificate sent to the exact
+    fp32 kernel.  Reads the device counters: synchronises."""
+    c = info.get("n_uncertified")
+    if c is None:
+        return None
+    return int(sum(int(t.item()) for t in (c if isinstance(c, (list, tuple)) else [c])))
 
 
 def tc_keep(kp: int) -> int:
@@ -188,67 +228,92 @@ class LemonScorer:
 
     # ------------------------------------------------------------------ K0
     def prepare(self, x, normalize: bool = True, need_f16: bool = True) -> Prepared:
-        x = _to_dev(x, self.device, torch.float32)
+        """K0.  `x` may be a row-strided 2-D device view (unit column stride), e.g. the embedding columns of a
+        wider all-gathered matrix: the kernel reads it in place."""
+        if not (torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+                and x.stride(0) >= x.shape[1]):
+            x = _to_dev(x, self.device, torch.float32)
         assert x.dim() == 2
         n, d = x.shape
         if d % 4:
             x = torch.nn.functional.pad(x, (0, 4 - d % 4))
             d = x.shape[1]
         d16 = -(-d // 64) * 64
-        out32 = torch.empty_like(x)
+        out32 = torch.empty((n, d), dtype=torch.float32, device=self.device)
         out16 = torch.empty((n, d16), dtype=torch.float16, device=self.device) if need_f16 else None
         row_stats = torch.empty((n, 4), dtype=torch.float32, device=self.device)
-        stats_max = torch.zeros(4, dtype=torch.float32, device=self.device)
+        stats_max = torch.empty(4, dtype=torch.float32, device=self.device)     # zeroed by the library call
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_normalize_cast(self.ctx.handle, _ptr(x), _ptr(out32), _ptr(out16),
-                                                         _ptr(row_stats), _ptr(stats_max), n, d, d16,
+                                                         _ptr(row_stats), _ptr(stats_max), n, d, d16, x.stride(0) if n > 1 else d,
                                                          int(bool(normalize)), _stream()), "lemon_normalize_cast")
         return Prepared(out32, out16, row_stats, stats_max, n, d, d16)
 
-    def find_duplicates(self, p: Prepared, min_saving: float = 0.1) -> "Dedup | None":
-        """Groups bit-identical rows (hash -> sort -> bit-wise verification).  Returns None when fewer than
-        `min_saving` of the rows are duplicates, or on a hash collision (then nothing is deduplicated)."""
+    def dedup_start(self, p: Prepared) -> "dict | None":
+        """Queues the device-side grouping of bit-identical rows (lemon_dedup_build: hash -> radix sort -> run scan ->
+        bit-wise verification -> renumbering) and an asynchronous read-back of its two counters.  No host
+        synchronisation happens here; ``dedup_finish`` waits for the counters."""
         n, dev = p.n, self.device
         if n < 64:
             return None
-        h = torch.empty(n, dtype=torch.int64, device=dev)
+        ws_bytes = int(self.lib.lemon_dedup_workspace_bytes(n))
+        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws = ws[(-ws.data_ptr()) % 256:]
+        pend = {"ws": ws, "rep": torch.empty(n, dtype=torch.int32, device=dev),
+                "members": torch.empty(n, dtype=torch.int32, device=dev),
+                "offsets": torch.empty(n + 1, dtype=torch.int64, device=dev),
+                "counters": torch.empty(2, dtype=torch.int32, device=dev),
+                "host": torch.empty(2, dtype=torch.int32).pin_memory(), "event": torch.cuda.Event()}
         with torch.cuda.device(dev):
-            self.ctx.check(self.lib.lemon_hash_rows(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(h), _stream()),
-                           "lemon_hash_rows")
-        hs, order = torch.sort(h, stable=True)            # equal hashes keep ascending row index
-        newg = torch.ones(n, dtype=torch.bool, device=dev)
-        newg[1:] = hs[1:] != hs[:-1]
-        n_u = int(newg.sum().item())
-        if n_u > (1.0 - min_saving) * n:
-            return None
-        gid_sorted = torch.cumsum(newg, 0) - 1             # group of every sorted position
-        rep_rows = order[torch.nonzero(newg).flatten()]    # lowest row index of each group
-        rep_of_row = torch.empty(n, dtype=torch.int64, device=dev)
-        rep_of_row[order] = rep_rows[gid_sorted]
-        flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        with torch.cuda.device(dev):
-            self.ctx.check(self.lib.lemon_rows_equal(self.ctx.handle, _ptr(p.f32), _ptr(rep_of_row), n, p.d, _ptr(flag),
-                                                     _stream()), "lemon_rows_equal")
-        if int(flag.item()) != 0:
-            return None                                    # 63-bit hash collision: do not deduplicate
-        perm = torch.argsort(rep_rows)                     # renumber groups by ascending representative index
-        inv = torch.empty_like(perm)
-        inv[perm] = torch.arange(n_u, device=dev)
-        new_gid = inv[gid_sorted]
-        o2 = torch.argsort(new_gid, stable=True)           # rows inside a group stay in ascending index order
-        members = order[o2].to(torch.int32).contiguous()
-        offsets = torch.zeros(n_u + 1, dtype=torch.int64, device=dev)
-        offsets[1:] = torch.cumsum(torch.bincount(new_gid, minlength=n_u), 0)
-        rep = rep_rows[perm]
-        uniq = Prepared(p.f32[rep].contiguous(), None if p.f16 is None else p.f16[rep].contiguous(),
-                        p.row_stats[rep].contiguous(), p.stats_max, n_u, p.d, p.d16)
-        return Dedup(uniq, offsets, members, n_u)
+            self.ctx.check(self.lib.lemon_dedup_build(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(pend["ws"]), _ptr(pend["rep"]),
+                                                      _ptr(pend["members"]), _ptr(pend["offsets"]), _ptr(pend["counters"]),
+                                                      _stream()), "lemon_dedup_build")
+        pend["host"].copy_(pend["counters"], non_blocking=True)
+        pend["event"].record()
+        return pend
 
-    def prepare_db(self, x, normalize: bool = True) -> Prepared:
-        """K0 + duplicate detection for one database matrix (run_lemon.py:163-164,175-176)."""
+    def dedup_finish(self, p: Prepared, pend: "dict | None", min_saving: float = 0.1) -> "Dedup | None":
+        """Reads the counters of ``dedup_start`` (the path's one host round trip: the number of unique rows sizes the
+        search operands).  Returns None when fewer than `min_saving` of the rows are duplicates, or on a hash
+        collision (then nothing is de-duplicated)."""
+        if pend is None:
+            return None
+        pend["event"].synchronize()
+        n_u, collision = int(pend["host"][0]), int(pend["host"][1])
+        pend.pop("ws")
+        if collision != 0 or n_u > (1.0 - min_saving) * p.n:
+            return None
+        dev = self.device
+        rep = pend["rep"][:n_u]
+
+        def gather(src, cols, dtype):
+            dst = torch.empty((n_u, cols), dtype=dtype, device=dev)
+            with torch.cuda.device(dev):
+                self.ctx.check(self.lib.lemon_gather_rows(self.ctx.handle, _ptr(src), _ptr(rep), None, n_u,
+                                                          cols * src.element_size(), _ptr(dst), _stream()), "lemon_gather_rows")
+            return dst
+        uniq = Prepared(gather(p.f32, p.d, torch.float32), None if p.f16 is None else gather(p.f16, p.d16, torch.float16),
+                        gather(p.row_stats, 4, torch.float32), p.stats_max, n_u, p.d, p.d16)
+        return Dedup(uniq, pend["offsets"][: n_u + 1], pend["members"], n_u)
+
+    def find_duplicates(self, p: Prepared, min_saving: float = 0.1) -> "Dedup | None":
+        return self.dedup_finish(p, self.dedup_start(p), min_saving)
+
+    def prepare_db(self, x, normalize: bool = True, defer_dedup: bool = False) -> Prepared:
+        """K0 + duplicate detection for one database matrix (run_lemon.py:163-164,175-176).  With defer_dedup the
+        grouping is only queued (``finish_db`` completes it), so that several matrices share one host round trip."""
         p = self.prepare(x, normalize, self.knn_mode != "exact")
         if self.dedup:
-            p.dedup = self.find_duplicates(p)
+            p._pending = self.dedup_start(p)
+            if not defer_dedup:
+                self.finish_db(p)
+        return p
+
+    def finish_db(self, p: Prepared) -> Prepared:
+        pend = getattr(p, "_pending", None)
+        if pend is not None:
+            p._pending = None
+            p.dedup = self.dedup_finish(p, pend)
         return p
 
     def rowwise_dist(self, a: torch.Tensor, b: torch.Tensor, metric: int) -> torch.Tensor:
@@ -310,12 +375,12 @@ class LemonScorer:
                    torch.empty((q.n, kp), dtype=torch.int32, device=self.device))
         top_val, top_idx = out
         uncert = torch.empty(max(q.n, 1), dtype=torch.int32, device=self.device)
-        n_unc = torch.zeros(1, dtype=torch.int32, device=self.device)
+        n_unc = torch.empty(1, dtype=torch.int32, device=self.device)           # zeroed by the library call
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_rerank(
                 self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
                 _ptr(q.row_stats) if use_bound else None, _ptr(db.stats_max) if use_bound else None,
-                C.c_float(ACC_EPS), q.n, db.n, db.d, cand_cnt.shape[1], kp, metric, _ptr(top_val), _ptr(top_idx),
+                C.c_float(acc_eps_coef(db.d16, db.d)), q.n, db.n, db.d, cand_cnt.shape[1], kp, metric, _ptr(top_val), _ptr(top_idx),
                 _ptr(uncert), _ptr(n_unc), _stream()), "lemon_rerank")
         return top_val, top_idx, uncert, n_unc
 
@@ -361,7 +426,7 @@ class LemonScorer:
             n_uncs.append(n_unc)
             nsegs.append(nseg)
         self.last_info = {"path": "tc", "nseg": nsegs[0] if len(nsegs) == 1 else nsegs,
-                          "n_uncertified": n_uncs[0] if len(n_uncs) == 1 else torch.stack(n_uncs).sum(0)}
+                          "n_uncertified": n_uncs}      # device counters, one per launch (sum them after a sync)
         return top_val, top_idx
 
     # ------------------------------------------------- run_lemon.py:163-176
@@ -422,33 +487,43 @@ class LemonScorer:
         self.last_info = {"img": info_n, "txt": info_m}
         return out
 
-    def emit(self, xq: Prepared, yq: Prepared, xdb: Prepared, ydb: Prepared, dists_tr, topn, topm, *, k: int, kp: int,
-             metric: int, qid=None, lab_q=None, lab_db=None, cls_emb=None, lab_noisy=None, n_class=None,
-             hparams: dict | None = None, return_records: bool = True) -> dict:
-        """K2b: per-sample records + score from exact top lists (run_lemon.py:250-307, utils.py:63-77)."""
-        nq = xq.n
-        db = {"x": xdb, "y": ydb, "dists_tr": dists_tr}
+    def alloc_outputs(self, nq: int, k: int, hparams, return_records: bool = True, index_dtype=torch.int64) -> dict:
         dev = self.device
-        f32 = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
-        out = {"d_1": f32(nq)}
+        out = {"d_1": torch.empty(nq, dtype=torch.float32, device=dev)}
         if return_records:
             for c in ("D_n", "dists_n", "dists_tr_n", "D_m", "dists_m", "dists_tr_m"):
-                out[c] = f32(nq, k)
-            out["I_n"] = torch.empty((nq, k), dtype=torch.int64, device=dev)
-            out["I_m"] = torch.empty((nq, k), dtype=torch.int64, device=dev)
-        hp_arr = None
+                out[c] = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            out["I_n"] = torch.empty((nq, k), dtype=index_dtype, device=dev)
+            out["I_m"] = torch.empty((nq, k), dtype=index_dtype, device=dev)
         if hparams is not None:
-            hp_arr = (C.c_double * 6)(*[float(hparams[key]) for key in HP_KEYS])
             for c in ("s_n", "s_m", "score"):
                 out[c] = torch.empty(nq, dtype=torch.float64, device=dev)
-        g = lambda name: _ptr(out.get(name))
-        with torch.cuda.device(dev):
+        return out
+
+    def emit(self, xq: Prepared, yq: Prepared, xdb: Prepared, ydb: Prepared, dists_tr, topn, topm, *, k: int, kp: int,
+             metric: int, qid=None, lab_q=None, lab_db=None, cls_emb=None, lab_noisy=None, n_class=None,
+             hparams: dict | None = None, return_records: bool = True, index_dtype=torch.int64, out: dict | None = None,
+             rows: tuple[int, int] | None = None) -> dict:
+        """K2b: per-sample records + score from exact top lists (run_lemon.py:250-307, utils.py:63-77).
+        `out` = tensors from alloc_outputs to write into; rows=(a, b) processes query rows [a, b) only (callers that
+        stream the results to the host launch it part by part)."""
+        nq = xq.n
+        if out is None:
+            out = self.alloc_outputs(nq, k, hparams, return_records, index_dtype)
+        a, b = (0, nq) if rows is None else rows
+        if b <= a:
+            return out
+        assert index_dtype in (torch.int64, torch.int32)
+        hp_arr = (C.c_double * 6)(*[float(hparams[key]) for key in HP_KEYS]) if hparams is not None else None
+        sl = lambda t: None if t is None else t[a:b]
+        g = lambda name: _ptr(sl(out.get(name)))
+        with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_score(
-                self.ctx.handle, _ptr(xq.f32), _ptr(yq.f32), _ptr(db["x"].f32), _ptr(db["y"].f32), _ptr(db["dists_tr"]),
-                _ptr(topn[0]), _ptr(topn[1]), _ptr(topm[0]), _ptr(topm[1]), _ptr(qid), _ptr(lab_q), _ptr(lab_db),
-                _ptr(cls_emb), _ptr(lab_noisy), int(n_class or 0), nq, db["x"].n, db["x"].d, k, kp, metric, hp_arr, g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"),
-                g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"), g("s_n"), g("s_m"), g("score"),
-                _stream()), "lemon_score")
+                self.ctx.handle, _ptr(xq.f32[a:b]), _ptr(yq.f32[a:b]), _ptr(xdb.f32), _ptr(ydb.f32), _ptr(dists_tr),
+                _ptr(topn[0][a:b]), _ptr(topn[1][a:b]), _ptr(topm[0][a:b]), _ptr(topm[1][a:b]), _ptr(sl(qid)), _ptr(sl(lab_q)),
+                _ptr(lab_db), _ptr(cls_emb), _ptr(sl(lab_noisy)), int(n_class or 0), b - a, xdb.n, xdb.d, k, kp, metric, hp_arr,
+                g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"), g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"),
+                64 if index_dtype == torch.int64 else 32, g("s_n"), g("s_m"), g("score"), _stream()), "lemon_score")
         return out
 
     def combine_scores(self, rec: dict, hparams: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -466,6 +541,24 @@ class LemonScorer:
                 _ptr(cols["dists_tr_m"]), _ptr(cols["dists_m"]), _ptr(d1), n, k, hp_arr, _ptr(sn), _ptr(sm), _ptr(sc),
                 _stream()), "lemon_combine_scores")
         return sc, sn, sm
+
+
+    def keep_lowest(self, score, n_keep: int):
+        """CC3M filtering step of train_clip_from_scratch.py:110-113 on the device: row ids (int64) of the `n_keep`
+        lowest scores in ascending score order (ties: lower row id first) and their scores."""
+        s = _to_dev(score, self.device, torch.float64).reshape(-1)
+        n = s.numel()
+        n_keep = int(min(max(n_keep, 0), n))
+        idx = torch.empty(n_keep, dtype=torch.int64, device=self.device)
+        val = torch.empty(n_keep, dtype=torch.float64, device=self.device)
+        if n_keep == 0:
+            return idx, val
+        ws = torch.empty(int(self.lib.lemon_keep_lowest_workspace_bytes(n)) + 256, dtype=torch.uint8, device=self.device)
+        ws = ws[(-ws.data_ptr()) % 256:]
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_keep_lowest(self.ctx.handle, _ptr(s), n, n_keep, _ptr(ws), _ptr(idx), _ptr(val),
+                                                      _stream()), "lemon_keep_lowest")
+        return idx, val
 
 
 _default_scorers: dict = {}

@@ -47,8 +47,12 @@ def normalize_vectors(v: np.ndarray) -> np.ndarray:
     """Row-wise ``x / max(||x||_2, 1e-12)`` in fp32 (lib/utils/utils.py:39-40 ->
     ``torch.nn.functional.normalize(p=2, dim=1)``)."""
     v = np.asarray(v, dtype=np.float32)
-    nrm = np.sqrt((v.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)
-    return (v / np.maximum(nrm, np.float32(1e-12))[:, None]).astype(np.float32)
+    out = np.empty_like(v)
+    for s in range(0, v.shape[0], 1 << 18):        # row blocks: no full-size float64 temporary
+        b = v[s:s + (1 << 18)]
+        nrm = np.sqrt((b.astype(np.float64) ** 2).sum(axis=1)).astype(np.float32)
+        out[s:s + (1 << 18)] = b / np.maximum(nrm, np.float32(1e-12))[:, None]
+    return out
 
 
 # --------------------------------------------------------------------------- a2
@@ -84,60 +88,82 @@ def dists_tr(emb_txt_tr: np.ndarray, emb_img_tr: np.ndarray, dist_type: str) -> 
 
 
 # --------------------------------------------------------------------------- a5
-def _topk_rows(S: np.ndarray, k: int, largest: bool) -> tuple[np.ndarray, np.ndarray]:
-    """Top-k of each row of S under the total order (best value first, then column
-    index ascending).  Exact on ties."""
+def _det_values(q64: np.ndarray, g64: np.ndarray, metric: str) -> np.ndarray:
+    """Deterministic float64 values of query rows [n,d] against gathered DB rows [n,c,d]: numpy's row-wise pairwise
+    summation depends only on the row CONTENT, so bit-identical DB rows get bit-identical values (a BLAS gemm does
+    not guarantee that: its result can depend on where a column sits in the matrix)."""
+    if metric == "ip":
+        return (q64[:, None, :] * g64).sum(-1)
+    return ((q64[:, None, :] - g64) ** 2).sum(-1)
+
+
+def _topk_chunk(q64: np.ndarray, db64: np.ndarray, S: np.ndarray, k: int, metric: str, pad: int = 32):
+    """Exact top-k of every row of the float64 similarity block S = f(q64, db64) under the total order (best value
+    first, then column index ascending).  The gemm values only pre-select k+pad candidates; their values are then
+    recomputed deterministically and ordered.  A row whose k-th value ties with the weakest candidate (mass ties
+    reaching past the candidate set) is redone with a full deterministic evaluation."""
     nq, m = S.shape
+    largest = metric == "ip"
     k_eff = min(k, m)
+    ncand = min(m, k_eff + pad)
     key = -S if largest else S
-    if m <= 4 * k_eff + 64:
-        order = np.argsort(key, axis=1, kind="stable")[:, :k_eff]
+    if ncand < m:
+        cand = np.argpartition(key, ncand - 1, axis=1)[:, :ncand]
     else:
-        pad = min(m - 1, k_eff + 32)
-        part = np.argpartition(key, pad, axis=1)[:, : pad + 1]
-        pk = np.take_along_axis(key, part, axis=1)
-        # sort the pad+1 survivors by (key, index)
-        o2 = np.lexsort((part, pk), axis=1)
-        part = np.take_along_axis(part, o2, axis=1)
-        pk = np.take_along_axis(pk, o2, axis=1)
-        order = part[:, :k_eff].copy()
-        # rows where the k-th value ties with the last survivor may have lost a
-        # lower-index tie outside the partition: redo them with a full stable sort
-        bad = np.nonzero(pk[:, k_eff - 1] == pk[:, pad])[0]
-        for r in bad:
-            order[r] = np.argsort(key[r], kind="stable")[:k_eff]
-    vals = np.take_along_axis(S, order, axis=1)
-    if k_eff < k:   # faiss pads I=-1, D=-inf (IP) / +inf (L2) when ntotal < k
-        padv = -np.inf if largest else np.inf
-        order = np.concatenate([order, np.full((nq, k - k_eff), -1, order.dtype)], axis=1)
-        vals = np.concatenate([vals, np.full((nq, k - k_eff), padv, vals.dtype)], axis=1)
-    return vals, order.astype(np.int64)
+        cand = np.broadcast_to(np.arange(m), (nq, m)).copy()
+    vals = np.empty((nq, ncand))
+    for s in range(0, nq, 256):
+        vals[s:s + 256] = _det_values(q64[s:s + 256], db64[cand[s:s + 256]], metric)
+    o = np.lexsort((cand, -vals if largest else vals), axis=1)
+    cand, vals = np.take_along_axis(cand, o, 1), np.take_along_axis(vals, o, 1)
+    if ncand < m:
+        for r in np.nonzero(np.abs(vals[:, k_eff - 1] - vals[:, -1]) <= 1e-12)[0]:
+            full = _det_values(q64[r:r + 1], db64[None], metric)[0]
+            oo = np.lexsort((np.arange(m), -full if largest else full))[:ncand]
+            cand[r], vals[r] = oo, full[oo]
+    return vals[:, :k_eff], cand[:, :k_eff].astype(np.int64)
 
 
 def knn_search(q: np.ndarray, db: np.ndarray, k: int, metric: str = "ip",
-               block: int = 2048) -> tuple[np.ndarray, np.ndarray]:
+               block: int = 2048, db_chunk: int = 131072) -> tuple[np.ndarray, np.ndarray]:
     """Exact brute-force kNN, float64 (stands in for faiss ``IndexFlatIP.search`` /
     ``IndexFlatL2.search`` at run_lemon.py:235-236).
 
     metric 'ip': D = <q,b>, descending.  metric 'l2': D = ||q-b||^2, ascending.
-    Returns (D float64 [nq,k], I int64 [nq,k])."""
-    q64 = np.ascontiguousarray(q, dtype=np.float64)
-    db64 = np.ascontiguousarray(db, dtype=np.float64)
-    nq = q64.shape[0]
-    D = np.empty((nq, k), dtype=np.float64)
-    I = np.empty((nq, k), dtype=np.int64)
-    dbn = (db64 ** 2).sum(axis=1) if metric == "l2" else None
+    Returns (D float64 [nq,k], I int64 [nq,k]); ``ntotal < k`` pads I=-1, D=-inf/+inf as faiss does.  The DB is
+    walked in chunks of `db_chunk` rows (only a chunk is ever held in float64, so multi-million-row databases fit
+    in host memory); every chunk yields its exact top-k under the total order (value best-first, then DB index
+    ascending) and the chunk lists are merged under the same order, which is exact."""
+    if metric not in ("ip", "l2"):
+        raise ValueError(metric)
+    q = np.asarray(q)
+    db = np.asarray(db)
+    nq, m = q.shape[0], db.shape[0]
+    largest = metric == "ip"
+    D = np.full((nq, k), -np.inf if largest else np.inf, dtype=np.float64)
+    I = np.full((nq, k), -1, dtype=np.int64)
+    block = max(1, min(block, int(2.5e8 // max(1, min(m, db_chunk)))))      # similarity block <= ~2 GB of float64
     for s in range(0, nq, block):
         e = min(nq, s + block)
-        S = q64[s:e] @ db64.T
-        if metric == "l2":
-            S = (q64[s:e] ** 2).sum(axis=1)[:, None] + dbn[None, :] - 2.0 * S
-            np.maximum(S, 0.0, out=S)
-            D[s:e], I[s:e] = _topk_rows(S, k, largest=False)
-        elif metric == "ip":
-            D[s:e], I[s:e] = _topk_rows(S, k, largest=True)
-        else:
-            raise ValueError(metric)
+        q64 = np.ascontiguousarray(q[s:e], dtype=np.float64)
+        best_v = best_i = None
+        for c0 in range(0, m, db_chunk):
+            c1 = min(m, c0 + db_chunk)
+            db64 = np.ascontiguousarray(db[c0:c1], dtype=np.float64)
+            S = q64 @ db64.T
+            if metric == "l2":      # pre-selection only: ||q||^2 + ||b||^2 - 2<q,b>, the expansion faiss uses
+                S = (q64 ** 2).sum(axis=1)[:, None] + (db64 ** 2).sum(axis=1)[None, :] - 2.0 * S
+            v, i = _topk_chunk(q64, db64, S, k, metric)
+            i = i + c0
+            if best_v is None:
+                best_v, best_i = v, i
+            else:                                  # merge two exact lists under (value best-first, index ascending)
+                av = np.concatenate([best_v, v], axis=1)
+                ai = np.concatenate([best_i, i], axis=1)
+                o = np.lexsort((ai, -av if largest else av), axis=1)[:, :k]
+                best_v, best_i = np.take_along_axis(av, o, 1), np.take_along_axis(ai, o, 1)
+        if best_v is not None:
+            D[s:e, :best_v.shape[1]], I[s:e, :best_v.shape[1]] = best_v, best_i
     return D, I
 
 
@@ -163,9 +189,9 @@ def build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type: s
     dists_tr_m (each [N,k])."""
     xq = np.asarray(img_q, np.float64)
     yq = np.asarray(txt_q, np.float64)
-    xdb = np.asarray(img_db, np.float64)
-    ydb = np.asarray(txt_db, np.float64)
-    dtr = dists_tr(txt_db, img_db, dist_type)
+    xdb = np.asarray(img_db)          # DB rows are gathered first and widened to float64 afterwards
+    ydb = np.asarray(txt_db)
+    dtr_rows = lambda I: dists_tr(ydb[I.reshape(-1)], xdb[I.reshape(-1)], dist_type).reshape(I.shape)
     discrete = text_label_ids_q is not None
     cos = dist_type == "cosine"
     N, k = I_n.shape
@@ -184,10 +210,10 @@ def build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type: s
             dists_n[s:e] = 1.0 - (np.asarray(text_label_ids_db)[I_n[s:e]]
                                   == np.asarray(text_label_ids_q)[s:e, None])
         else:
-            y_n = ydb[I_n[s:e]]                                               # :264
+            y_n = ydb[I_n[s:e]].astype(np.float64)                            # :264
             dists_n[s:e] = (1.0 - np.einsum("nd,nkd->nk", yq[s:e], y_n)) if cos else \
                 ((yq[s:e, None, :] - y_n) ** 2).sum(-1)                       # :270-273
-        x_m = xdb[I_m[s:e]]                                                   # :284
+        x_m = xdb[I_m[s:e]].astype(np.float64)                                # :284
         dists_m[s:e] = (1.0 - np.einsum("nd,nkd->nk", xq[s:e], x_m)) if cos else \
             ((xq[s:e, None, :] - x_m) ** 2).sum(-1)                           # :286-289
     Dn = np.asarray(D_n, np.float64).copy()
@@ -196,8 +222,8 @@ def build_records(img_q, txt_q, img_db, txt_db, D_n, I_n, D_m, I_m, dist_type: s
         if not discrete:
             Dn = -Dn          # :270 (sits in the else-branch: skipped for the discrete metric)
         Dm = -Dm              # :286
-    return {"d_1": d_1, "D_n": Dn, "dists_n": dists_n, "dists_tr_n": dtr[I_n],
-            "D_m": Dm, "dists_m": dists_m, "dists_tr_m": dtr[I_m]}
+    return {"d_1": d_1, "D_n": Dn, "dists_n": dists_n, "dists_tr_n": dtr_rows(I_n),
+            "D_m": Dm, "dists_m": dists_m, "dists_tr_m": dtr_rows(I_m)}
 
 
 # ------------------------------------------------------------------------- a11
@@ -274,12 +300,12 @@ def lemon_oracle(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str = "cosi
 def pair_values(q, db, I, metric: str) -> np.ndarray:
     """float64 similarity / squared distance of each query to the listed DB rows."""
     q64 = np.asarray(q, np.float64)
-    db64 = np.asarray(db, np.float64)
+    db = np.asarray(db)
     out = np.empty(I.shape, np.float64)
     bs = 1024
     for s in range(0, I.shape[0], bs):
         e = min(I.shape[0], s + bs)
-        g = db64[I[s:e]]
+        g = db[I[s:e]].astype(np.float64)
         if metric == "ip":
             out[s:e] = np.einsum("nd,nkd->nk", q64[s:e], g)
         else:

@@ -40,6 +40,30 @@ def iid_pairs(n, d, seed=0):
     return x.astype(np.float32), y.astype(np.float32)
 
 
+KNN_PIN_CASES = ("a", "b", "c", "u", "t")
+
+
+def knn_pin_case(tag):
+    """Seeded inputs of the independent kNN answers in tests/golden/knn.npz (make_golden_knn.py).
+    Returns (db, q, k, kind); numpy's legacy RandomState stream is frozen, so the arrays are reproducible."""
+    rng = np.random.RandomState({"a": 101, "b": 102, "c": 103, "u": 104, "t": 105}[tag])
+    unit = lambda a: (a / np.linalg.norm(a, axis=1, keepdims=True)).astype(np.float32)
+    if tag in ("a", "b", "c"):
+        m, nq, d, k = {"a": (3000, 96, 64, 31), "b": (2500, 64, 96, 30), "c": (4096, 48, 512, 51)}[tag]
+        cen = rng.standard_normal((20, d))
+        db = unit(cen[rng.randint(0, 20, m)] + 0.7 * rng.standard_normal((m, d)))
+        q = unit(db[rng.choice(m, nq, replace=False)] + 0.05 * rng.standard_normal((nq, d)))
+        return db, q, k, "unit"
+    if tag == "u":
+        m, nq, d, k = 2200, 80, 128, 31
+        db = (rng.standard_normal((m, d)) * rng.uniform(0.5, 3.0, (m, 1)) / np.sqrt(d)).astype(np.float32)
+        q = (rng.standard_normal((nq, d)) * rng.uniform(0.5, 3.0, (nq, 1)) / np.sqrt(d)).astype(np.float32)
+        return db, q, k, "raw"
+    base = unit(rng.standard_normal((40, 64)))
+    db = np.repeat(base, 25, axis=0)[rng.permutation(1000)]     # every vector 25 times, shuffled: mass ties
+    return db, base[:16].copy(), 31, "ties"
+
+
 def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_in_db=None, hparams=None,
                          lab_q=None, lab_db=None, eps_tie=None, rtol=1e-5, normalize=True):
     """Acceptance check of SURVEY.md §8c for a score_pairs() result `out` (numpy arrays):

@@ -1,5 +1,5 @@
 """CPU tests of the row-sharding plumbing with the gloo backend (world_size 2).  The scorer is replaced
-by a stand-in that evaluates the oracle, so the N>1 host path (shard bounds, padding, the two
+by a CPU scorer with the same staged interface that evaluates the oracle, so the N>1 host path (shard bounds, padding, the two
 all-gathers, global query ids) is exercised without a GPU."""
 import os
 import socket
@@ -26,19 +26,44 @@ def test_shard_bounds_cover_everything():
 
 
 class OracleScorer:
-    """Stand-in with the LemonScorer interface used by score_pairs_sharded."""
+    """CPU scorer with the staged interface score_pairs_sharded drives (prepare_db / finish_db / knn / rowwise_dist /
+    emit on ``Prepared`` operands), every stage evaluated by the oracle."""
+    device = torch.device("cpu")
 
-    def set_database(self, img_db, txt_db, dist_type, normalize, labels):
-        self.db = (img_db.numpy(), txt_db.numpy(), dist_type, normalize)
+    def __init__(self):
+        self.last_info = {}
 
-    def score(self, img_q, txt_q, *, k, query_in_db, hparams, return_records, query_rows, text_label_ids_q):
+    def prepare_db(self, x, normalize=True, defer_dedup=False):
+        from lemon_b200.scoring import Prepared
         from oracle import lemon_oracle as O
-        x, y, dist_type, normalize = self.db
-        r0, r1 = query_rows
-        assert query_in_db.tolist() == list(range(r0, r1))
-        out = O.lemon_oracle(x[r0:r1], y[r0:r1], x, y, k=k, dist_type=dist_type, query_in_db=query_in_db.numpy(),
-                             hparams=hparams, normalize=normalize)
-        return {c: torch.from_numpy(np.asarray(out[c])) for c in ("score", "I_n", "I_m", "d_1")}
+        a = x.numpy()
+        a = O.normalize_vectors(a) if normalize else a.astype(np.float32)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return Prepared(t, None, torch.zeros(len(a), 4), torch.zeros(4), t.shape[0], t.shape[1], t.shape[1])
+
+    def finish_db(self, p):
+        return p
+
+    def knn(self, q, db, kp, metric):
+        from oracle import lemon_oracle as O
+        D, I = O.knn_search(q.f32.numpy(), db.f32.numpy(), kp, "ip" if metric == 0 else "l2")
+        self.last_info = {"path": "oracle"}
+        return torch.from_numpy(D), torch.from_numpy(I.astype(np.int32))
+
+    def rowwise_dist(self, a, b, metric):
+        from oracle import lemon_oracle as O
+        return torch.from_numpy(O.dists_tr(a.numpy(), b.numpy(), "cosine" if metric == 0 else "euclidean"))
+
+    def emit(self, xq, yq, xdb, ydb, dists_tr, topn, topm, *, k, kp, metric, qid, hparams, **_):
+        from oracle import lemon_oracle as O
+        dist_type = "cosine" if metric == 0 else "euclidean"
+        in_db = qid.numpy() >= 0
+        Dn, In = O.apply_self_exclusion(topn[0].numpy(), topn[1].numpy().astype(np.int64), in_db)
+        Dm, Im = O.apply_self_exclusion(topm[0].numpy(), topm[1].numpy().astype(np.int64), in_db)
+        rec = O.build_records(xq.f32.numpy(), yq.f32.numpy(), xdb.f32.numpy(), ydb.f32.numpy(), Dn, In, Dm, Im, dist_type)
+        score, sn, sm = O.calc_scores_vectorized(rec, hparams)
+        return {"score": torch.from_numpy(score), "I_n": torch.from_numpy(In), "I_m": torch.from_numpy(Im),
+                "d_1": torch.from_numpy(rec["d_1"])}
 
 
 def _worker(rank, world, port, n, d, k, q):

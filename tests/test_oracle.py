@@ -84,14 +84,21 @@ def test_knn_orthonormal_and_ties():
     assert I4[0].tolist()[2:] == [-1, -1] and np.isinf(D4[0, 2:]).all()
 
 
-def test_topk_partition_path_matches_full_sort():
+def test_knn_mass_ties_and_chunking_follow_the_total_order():
+    """Bit-identical DB rows far beyond the candidate padding, straddling the k-th boundary and DB-chunk borders:
+    the result is the full stable sort (best value, then ascending index) whatever the chunking."""
     rng = np.random.RandomState(3)
-    S = rng.rand(7, 5000)
-    S[2, 100:300] = 0.99999      # mass tie straddling the boundary
-    S[2, :5] = 2.0
-    v, o = O._topk_rows(S, 40, largest=True)
-    ref = np.argsort(-S, axis=1, kind="stable")[:, :40]
-    assert (o == ref).all()
+    db = rng.standard_normal((5000, 24)).astype(np.float32)
+    db[100:300] = db[7]            # 201 copies of one row
+    q = np.concatenate([db[7:8], db[:6]])
+    for metric in ("ip", "l2"):
+        q64, db64 = q.astype(np.float64), db.astype(np.float64)
+        full = O._det_values(q64, np.broadcast_to(db64, (len(q),) + db64.shape), metric)
+        ref = np.argsort(-full if metric == "ip" else full, axis=1, kind="stable")[:, :40]
+        for kw in ({}, {"db_chunk": 150}, {"db_chunk": 64, "block": 3}):
+            D, I = O.knn_search(q, db, 40, metric, **kw)
+            assert (I == ref).all(), (metric, kw)
+    assert O.knn_search(q, db, 40, "ip")[1][0, :5].tolist() == [7, 100, 101, 102, 103]
 
 
 def test_conventions_cosine_and_euclid():

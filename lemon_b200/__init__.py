@@ -5,7 +5,10 @@ Public surface (mirrors the reference's seams):
   LemonScorer                                       set_database / score / knn / combine_scores
   faiss_compat.IndexFlatIP / IndexFlatL2            drop-in for the faiss calls at run_lemon.py:167-176,235-236
   metrics_compat.calc_scores_given_hparams_vectorized   drop-in for lib/metrics/utils.py:47-82
-  dist.score_pairs_sharded                          row-sharded multi-GPU driver (one NCCL all-gather)
+  dist.score_pairs_sharded                          row-sharded multi-GPU driver (one NCCL all-gather per modality)
+  handoff.extract_and_score                         encoder outputs -> device shard -> staged database -> scores (no host copy)
+  subsample_db / query_in_db_from_indices           the reference's DB cap (run_lemon.py:48,122-127) and membership rule
+  filter_lowest_scores                              CC3M consumer of the scores (train_clip_from_scratch.py:110-113)
 """
 from . import _lib
 from ._lib import LemonError, LIB_PATH

@@ -13,7 +13,7 @@ METHODS = ("dis_x", "dis_y", "div_x", "div_y")
 
 
 def discrepancy_scores(img_q, txt_q, img_db, txt_db, *, k: int, method: str, train: bool = False, normalize: bool = True,
-                       device=None) -> torch.Tensor:
+                       device=None, return_lists: bool = False):
     """pred_score of discrepancy_baseline.py for every query pair (float32 [N]).  `train=True` searches k+1 text
     neighbours as the script does for the train split (it keeps all k+1, :210-215)."""
     assert method in METHODS
@@ -36,4 +36,6 @@ def discrepancy_scores(img_q, txt_q, img_db, txt_db, *, k: int, method: str, tra
         sc.ctx.check(sc.lib.lemon_discrepancy(sc.ctx.handle, _ptr(emb.f32), _ptr(qemb.f32) if qemb is not None else None,
                                               _ptr(nn), _ptr(cache), yq.n, ydb.n, emb.d, kk, kc, k, mode, _ptr(out),
                                               _stream()), "lemon_discrepancy")
+    if return_lists:        # the text-kNN list of every query and (dis_*) of every DB row, as searched
+        return out, nn, cache
     return out

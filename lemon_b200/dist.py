@@ -136,21 +136,38 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     scorer.finish_db(xdb)
     if ydb is not None:
         scorer.finish_db(ydb)
+    lab_db = txt_all[:, d].contiguous().view(torch.int32) if with_labels else None
+    finish_text = None
+    if ydb is None:
+        def finish_text():
+            main.wait_event(e_txt)
+            return scorer.finish_db(stage_text_db()), (txt_all[:, d].contiguous().view(torch.int32) if with_labels else None)
+    return score_staged(scorer, xdb, ydb, (r0, r1, per), k=k, metric=metric, hparams=hparams, return_records=return_records,
+                        lab_db=lab_db, host_out=host_out, index_dtype=index_dtype, d2h_parts=d2h_parts, late_text=finish_text)
+
+
+def score_staged(scorer, xdb, ydb, bounds, *, k: int, metric: int, hparams=None, return_records: bool = True, lab_db=None,
+                 host_out: dict | None = None, index_dtype=torch.int64, d2h_parts: int = 4, late_text=None) -> dict:
+    """Second half of the sharded path on STAGED databases (K0 done, duplicate grouping finished): kNN of this rank's
+    rows against both replicated databases, dists_tr, records + score.  `late_text` (host-input path) stages the text
+    database after the image-side kNN has been queued."""
+    from .scoring import _slice_prepared
+    r0, r1, per = bounds
+    dev = scorer.device
+    on_gpu = dev.type == "cuda"
+    main = torch.cuda.current_stream(dev) if on_gpu else None
+    kp = k + 1
     xq = _slice_prepared(xdb, r0, r1)
     topn = scorer.knn(xq, xdb, kp, metric)
     info_n = scorer.last_info
     # ---- text side
     if ydb is None:
-        main.wait_event(e_txt)
-        ydb = scorer.finish_db(stage_text_db())
+        ydb, lab_db = late_text()
     yq = _slice_prepared(ydb, r0, r1)
     dtr = scorer.rowwise_dist(ydb.f32, xdb.f32, metric)
     topm = scorer.knn(yq, ydb, kp, metric)
     info_m = scorer.last_info
-    lab_db = lab_q = None
-    if with_labels:
-        lab_db = txt_all[:, d].contiguous().view(torch.int32)
-        lab_q = lab_db[r0:r1]
+    lab_q = lab_db[r0:r1] if lab_db is not None else None
     qid = _global_row_ids(scorer, r0, r1)
     nq = r1 - r0
     common = dict(k=k, kp=kp, metric=metric, qid=qid, lab_q=lab_q, lab_db=lab_db, hparams=hparams,

@@ -358,7 +358,7 @@ def compare_neighbor_sets(q, db, I_got: np.ndarray, k: int, metric: str = "ip",
 def reference_cpu_scorer(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str = "cosine",
                          train_indices_in_compr=None, sample_offset: int = 0,
                          hparams: dict | None = None, batch_size: int = 128,
-                         score_fn=None):
+                         score_fn=None, faiss_module=None, timings: dict | None = None):
     """Operation-for-operation port of the reference CPU scorer, used ONLY as the timed
     CPU baseline (bench.py cpu_baseline / --impl reference).
 
@@ -368,9 +368,17 @@ def reference_cpu_scorer(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str
     same BLAS class, same complexity) -> the per-sample Python loop with its tiny
     torch ops and dict/array allocations (:238-307) -> ``pd.DataFrame`` (:314) ->
     ``calc_scores_given_hparams_vectorized`` (utils.py:47-82; ``score_fn`` may be the
-    live reference function).  train_indices_in_compr=None means a val/test split."""
+    live reference function).  train_indices_in_compr=None means a val/test split.
+
+    faiss_module: a module with the faiss API (``IndexFlatIP/IndexFlatL2.add/search``); when given, the index build
+    and the per-batch searches go through it exactly as run_lemon.py:166-176,235-236 call faiss (the seam test
+    passes ``lemon_b200.faiss_compat``).  timings: dict that receives 'prep_s' (normalise + index build: paid once
+    per database) and 'query_s' (everything per query batch + DataFrame + scoring)."""
+    import time
     import torch
     import pandas as pd
+
+    t_start = time.perf_counter()
 
     F = torch.nn.functional
     emb_txt_tr = F.normalize(torch.as_tensor(txt_db, dtype=torch.float32), p=2, dim=1)
@@ -387,8 +395,19 @@ def reference_cpu_scorer(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str
         n_txt = (emb_txt_tr ** 2).sum(1)
     train = train_indices_in_compr is not None
     kk = k + int(train)
+    if faiss_module is not None:
+        d = emb_img_tr.shape[1]
+        index_img = faiss_module.IndexFlatIP(d) if cos else faiss_module.IndexFlatL2(d)      # run_lemon.py:167-168 / 171-172
+        index_txt = faiss_module.IndexFlatIP(d) if cos else faiss_module.IndexFlatL2(d)
+        index_img.add(emb_img_tr.numpy())                                                    # :175-176
+        index_txt.add(emb_txt_tr.numpy())
+    t_prep = time.perf_counter()
 
     def search(qb, db_t, nrm):
+        if faiss_module is not None:
+            index = index_img if db_t is db_img_t else index_txt
+            Dq, Iq = index.search(qb.numpy(), kk)                                            # :235-236
+            return torch.from_numpy(Dq), torch.from_numpy(Iq)
         ip = qb @ db_t
         if cos:
             return torch.topk(ip, kk, dim=1)
@@ -450,4 +469,7 @@ def reference_cpu_scorer(img_q, txt_q, img_db, txt_db, *, k: int, dist_type: str
             df["score"] = calc_scores_vectorized(rec, hparams)[0]
         else:
             df["score"] = score_fn(df, hparams)
+    if timings is not None:
+        timings["prep_s"] = t_prep - t_start
+        timings["query_s"] = time.perf_counter() - t_prep
     return df

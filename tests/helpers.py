@@ -40,6 +40,25 @@ def iid_pairs(n, d, seed=0):
     return x.astype(np.float32), y.astype(np.float32)
 
 
+def hparam_search_case(tag):
+    """Small LEMoN-like validation DataFrame + search arguments (run_lemon.py:331-394 in miniature) shared by
+    tests/golden/make_golden_hparam_search.py and tests/test_hparam_search.py."""
+    import pandas as pd
+    from oracle import lemon_oracle as O
+    n, k = 240, 6
+    x, y, _, mis = clustered_pairs(n, 40, n_clusters=8, seed=77, noise_frac=0.35)
+    o = O.lemon_oracle(x, y, x, y, k=k, query_in_db=np.arange(n))
+    cols = ("D_n", "D_m", "dists_tr_n", "dists_tr_m", "dists_n", "dists_m")
+    rec = {c: o[c].astype(np.float32) for c in cols}
+    d1 = o["d_1"].astype(np.float32).astype(np.float64)
+    df = pd.DataFrame([{**{c: rec[c][i] for c in cols}, "d_1": float(d1[i]), "is_mislabel": int(mis[i])} for i in range(n)])
+    grid = {"beta": np.arange(0, 20.01, 10), "gamma": np.arange(0, 20.01, 10), "tau_1": [0, 5], "tau_2": [0, 5]}
+    x0s = [[0] * 6, [0.5] * 6]
+    if tag == "ablate":          # run_lemon.py:364-377: --ablation d1_gamma
+        return df, grid, x0s, ["gamma"], ["beta"]
+    return df, grid, x0s, [], []
+
+
 KNN_PIN_CASES = ("a", "b", "c", "u", "t")
 
 
@@ -65,11 +84,12 @@ def knn_pin_case(tag):
 
 
 def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_in_db=None, hparams=None,
-                         lab_q=None, lab_db=None, eps_tie=None, rtol=1e-5, normalize=True):
+                         lab_q=None, lab_db=None, eps_tie=None, rtol=1e-5, normalize=True, strict=True):
     """Acceptance check of SURVEY.md §8c for a score_pairs() result `out` (numpy arrays):
     neighbour SETS equal the float64 oracle's modulo eps-ties at the boundary; record arrays and
     scores within `rtol` of the oracle — rows whose sets differ by an excused tie are compared
-    with the oracle re-evaluated on the returned index sets.  Returns counts."""
+    with the oracle re-evaluated on the returned index sets.  Returns counts.  strict=False (bench.py's
+    parity gate) counts wrong rows / mismatching values in stats["wrong"] instead of raising."""
     from oracle import lemon_oracle as O
     metric = "ip" if dist_type == "cosine" else "l2"
     if eps_tie is None:
@@ -79,8 +99,19 @@ def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_
     ref = O.lemon_oracle(xq, yq, xdb, ydb, k=k, dist_type=dist_type, query_in_db=query_in_db, hparams=hparams,
                          normalize=False, text_label_ids_q=lab_q, text_label_ids_db=lab_db)
     N = xq.shape[0]
-    stats = {}
+    stats = {"wrong": 0}
     tie_rows = np.zeros(N, bool)
+    bad_rows = np.zeros(N, bool)
+
+    def close(a, b, atol, what):
+        """assert_allclose, or (strict=False) mark the rows that violate it"""
+        if strict:
+            np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=what)
+            return
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        viol = ~(np.abs(a - b) <= atol + rtol * np.abs(b))
+        viol |= np.isnan(a) != np.isnan(b)
+        return viol.any(axis=tuple(range(1, viol.ndim))) if viol.ndim > 1 else viol
     for side, q, db in (("n", xq, xdb), ("m", yq, ydb)):
         I_got = out[f"I_{side}"]
         assert I_got.shape == (N, k) and I_got.dtype == np.int64
@@ -93,7 +124,9 @@ def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_
             top = np.where(np.asarray(query_in_db) >= 0, raw_D[:, 0], np.nan)
         r = O.compare_neighbor_sets(q, db, I_got, k, metric, eps_tie=eps_tie, D_ref=D_ref, I_ref=ref[f"I_{side}"],
                                     top_boundary=top)
-        assert r["wrong"] == 0, f"side {side}: {r['wrong']} rows with wrong neighbour sets, e.g. {r['wrong_rows'][:5]}"
+        if strict:
+            assert r["wrong"] == 0, f"side {side}: {r['wrong']} rows with wrong neighbour sets, e.g. {r['wrong_rows'][:5]}"
+        bad_rows[r["wrong_rows"]] = True
         stats[f"exact_{side}"], stats[f"tie_excused_{side}"] = r["exact"], r["tie_excused"]
         tie_rows[r["excused_rows"]] = True
     # rows with tie-excused sets: oracle re-evaluated on the returned sets
@@ -109,14 +142,26 @@ def check_against_oracle(out, xq, yq, xdb, ydb, *, k, dist_type="cosine", query_
         orf = np.argsort(ref[f"I_{side}"], axis=1, kind="stable")
         a = np.take_along_axis(out[c].astype(np.float64), og, axis=1)
         b = np.take_along_axis(ref[c], orf, axis=1)
-        ok = ~tie_rows
-        np.testing.assert_allclose(a[ok], b[ok], rtol=rtol, atol=2e-6, err_msg=c)
-        np.testing.assert_allclose(out[c][tie_rows].astype(np.float64), ref2[c][tie_rows], rtol=rtol, atol=2e-6,
-                                   err_msg=c + " (tie rows)")
-    np.testing.assert_allclose(out["d_1"], ref["d_1"], rtol=rtol, atol=2e-6)
+        ok = ~tie_rows & ~bad_rows
+        tr = tie_rows & ~bad_rows
+        v1 = close(a[ok], b[ok], 2e-6, c)
+        v2 = close(out[c][tr].astype(np.float64), ref2[c][tr], 2e-6, c + " (tie rows)")
+        if not strict:
+            bad_rows[np.nonzero(ok)[0][v1]] = True
+            bad_rows[np.nonzero(tr)[0][v2]] = True
+    v = close(out["d_1"], ref["d_1"], 2e-6, "d_1")
+    if not strict:
+        bad_rows |= v
     if hparams is not None:
         for c in ("s_n", "s_m", "score"):
-            np.testing.assert_allclose(out[c][~tie_rows], ref[c][~tie_rows], rtol=rtol, atol=1e-6, err_msg=c)
-            np.testing.assert_allclose(out[c][tie_rows], ref2[c][tie_rows], rtol=rtol, atol=1e-6, err_msg=c + " (tie rows)")
+            ok = ~tie_rows & ~bad_rows
+            tr = tie_rows & ~bad_rows
+            v1 = close(out[c][ok], ref[c][ok], 1e-6, c)
+            v2 = close(out[c][tr], ref2[c][tr], 1e-6, c + " (tie rows)")
+            if not strict:
+                bad_rows[np.nonzero(ok)[0][v1]] = True
+                bad_rows[np.nonzero(tr)[0][v2]] = True
     stats["tie_rows"] = int(tie_rows.sum())
+    stats["wrong"] = int(bad_rows.sum())
+    stats["wrong_rows"] = np.nonzero(bad_rows)[0][:16].tolist()
     return stats

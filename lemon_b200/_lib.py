@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblemon_b200.so")
+# LEMON_B200_LIB: developer override (e.g. a build with -DLEMON_TC_EXPERIMENT for kernel experiments)
+LIB_PATH = os.environ.get("LEMON_B200_LIB") or os.path.join(_HERE, "liblemon_b200.so")
 
 c_f32p = C.c_void_p
 c_i32p = C.c_void_p

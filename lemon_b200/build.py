@@ -32,16 +32,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out_path: str | None = None) -> str:
+    """out_path: alternative output path (objects go to a sibling directory), for experimental builds."""
+    if out_path is None and not force and not needs_build():
         return OUT
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
     flags += os.environ.get("LEMON_BUILD_DEFS", "").split()      # e.g. -DLEMON_TC_PROFILE (in-kernel clock counters of K1)
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objdir = os.path.join(HERE, "build") if out_path is None else out_path + ".objs"
+    os.makedirs(objdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *flags, *EXTRA_FLAGS.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -55,10 +57,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs]
+    target = OUT if out_path is None else out_path
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", target, *objs]
     subprocess.run(cmd, check=True)
-    return OUT
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    out_arg = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out_path=out_arg))

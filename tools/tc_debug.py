@@ -7,14 +7,15 @@ import lemon_b200
 from tests.helpers import iid_pairs, clustered_pairs
 
 cg, nq, m, d = (int(a) for a in sys.argv[1:5])
-nseg = int(sys.argv[5]) if len(sys.argv) > 5 else 1
+nseg = int(sys.argv[5]) if len(sys.argv) > 5 and not sys.argv[5].startswith("-") else 1
+KEEP = int(os.environ.get("K1_KEEP", "40"))     # score_pairs passes keep = 40 for k = 30
 sc = lemon_b200.get_scorer()
 x, _, _, _ = clustered_pairs(m, d, n_clusters=max(4, m // 100), seed=1)
 q = x[:nq].copy() if nq <= m else iid_pairs(nq, d, seed=2)[0]
 qp, dbp = sc.prepare(q, True), sc.prepare(x, True)
 torch.cuda.synchronize()
 t0 = time.time()
-ck, cc, ct, nseg = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+ck, cc, ct, nseg = sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg, keep=KEEP)
 torch.cuda.synchronize()
 print(f"cg={cg} nq={nq} m={m} d={d} nseg={nseg}: kernel returned in {time.time()-t0:.3f}s")
 if nq * m > 6e8:
@@ -42,11 +43,11 @@ if S is not None:
   Sn = S.cpu().numpy().copy(); np.put_along_axis(Sn, np.where(ci_h < 0, 0, ci_h), -np.inf, 1)
   print('max over unlisted columns of (S - theta_max):', float((Sn.max(1) - th).max()))
 if "--time" in sys.argv:
-    for _ in range(3): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+    for _ in range(3): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg, keep=KEEP)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
-    for _ in range(5): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg)
+    for _ in range(5): sc.knn_candidates(qp, dbp, nseg=nseg, cta_group=cg, keep=KEEP)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
-    print(f"time {ms:.3f} ms  -> {2.0*nq*m*dbp.d16/ms/1e9:.1f} TFLOP/s")
+    print(f"time {ms:.3f} ms  -> {2.0*nq*m*dbp.d16/ms/1e9:.1f} TFLOP/s   mean list length {float(cc[:nq].float().mean()):.1f}")

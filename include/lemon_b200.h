@@ -49,7 +49,8 @@ enum lemon_metric { LEMON_METRIC_IP = 0, LEMON_METRIC_L2 = 1 };
 #define LEMON_KPRIME 64          /* a row's candidate lists together hold its 64 best approximate values */
 #define LEMON_LIST_CAP 1024      /* slots per candidate list */
 #define LEMON_MAX_KP 64          /* largest k (+1 for self-exclusion) a top list can hold */
-#define LEMON_MAX_D_TC 768       /* largest padded dim the tensor-core kernel keeps resident */
+#define LEMON_MAX_D_TC 768       /* largest padded embedding dim served by the tensor-core path */
+#define LEMON_MAX_D16_OPERAND (3 * LEMON_MAX_D_TC)   /* widest K1 operand: the split-precision second pass is 3 x d16 wide */
 
 int lemon_version(void);
 int lemon_ctx_create(int device, lemon_ctx** out);
@@ -69,13 +70,25 @@ int lemon_normalize_cast(lemon_ctx* ctx, const float* in, float* out_f32, void* 
                          float* row_stats, float* stats_max, int64_t n, int d, int d16,
                          int64_t in_stride, int do_normalize, void* stream);
 
+/* Split-precision operands for the second tensor-core pass over rows the first pass could not certify.
+ *   x [n, d] fp32 (already normalised) = x_hi + x_lo + x_e with x_hi = fp16(x), x_lo = fp16(x - x_hi)
+ *   out_f16 [n, 3*d16]: role 0 (queries) [hi | hi | lo], role 1 (database) [hi | lo | hi]; one lemon_knn_candidates
+ *   call over these 3*d16-wide operands accumulates q_hi.b_hi + q_hi.b_lo + q_lo.b_hi in fp32, whose distance to the
+ *   exact inner product is bounded by ||q_e|| max||b|| + ||q|| max||b_e|| + (accumulation + the q_lo.b_lo term) --
+ *   a few 1e-5 instead of the ~6e-4 of one fp16 word per operand.
+ *   row_stats [n,4] = {||x||, ||x||, ||x_e||, ||x||^2}, stats_max [4] = their maxima (last: | ||x||^2 - 1 |), in the
+ *   layout lemon_rerank reads (either may be NULL).
+ */
+int lemon_split_cast(lemon_ctx* ctx, const float* x, void* out_f16, float* row_stats, float* stats_max,
+                     int64_t n, int d, int d16, int role, void* stream);
+
 /* out[i] = 1 - <a_i, b_i> (metric IP / cosine)  or  sum (a_i - b_i)^2 (metric L2). run_lemon.py:169,173,250-253 */
 int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* out,
                        int64_t n, int d, int metric, void* stream);
 
 /* Tensor-core candidate search (K1): fp16 operands, fp32 TMEM accumulation, streaming top-k fused into the
  * epilogue; the nq x m similarity matrix never reaches HBM.
- *   q16  [nq, d16], db16 [m, d16]  fp16 row-major, d16 % 64 == 0, d16 <= LEMON_MAX_D_TC
+ *   q16  [nq, d16], db16 [m, d16]  fp16 row-major, d16 % 64 == 0, d16 <= LEMON_MAX_D16_OPERAND
  *   nseg  number of DB segments scanned independently (load balance for small nq); >= 1
  *   Output = LEMON_NLIST(nseg) = nseg * 2 candidate lists per query row (two epilogue warp groups per segment).
  *   nq_pad = nq rounded up to a multiple of 256 rows; the caller allocates all three arrays for nq_pad rows:
@@ -110,11 +123,13 @@ int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int6
  *   top_val / top_idx [nq, kp]: exact top list.  A row is certified when its kp-th exact value beats every
  *   non-candidate's bound (max over lists of cand_theta, + eps_row); otherwise its row id is appended to
  *   uncert_rows[0 .. *n_uncert) (*n_uncert is zeroed by the call, on the stream; room for nq ids).
+ *   out_rows [nq] int32 or NULL: query row r writes row out_rows[r] of top_val / top_idx and reports that id when
+ *   uncertified (second-pass calls on a gathered subset of the rows).
  */
 int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const uint64_t* cand_keys,
                  const int32_t* cand_cnt, const float* cand_theta, const float* q_row_stats,
                  const float* db_stats_max, float acc_eps, int64_t nq, int64_t m, int d, int nlist, int kp,
-                 int metric, float* top_val, int32_t* top_idx, int32_t* uncert_rows,
+                 int metric, const int32_t* out_rows, float* top_val, int32_t* top_idx, int32_t* uncert_rows,
                  int32_t* n_uncert, void* stream);
 
 /* fp32 brute-force exact kNN on CUDA cores (GPU fallback for uncertified rows, and the

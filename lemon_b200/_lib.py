@@ -31,8 +31,10 @@ SIGNATURES = {
     "lemon_knn_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                        C.c_int, C.c_int, c_i64p, c_i32p, c_f32p, C.c_void_p]),
     "lemon_rerank": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i64p, c_i32p, c_f32p, c_f32p, c_f32p, C.c_float,
-                               C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_f32p, c_i32p, c_i32p,
+                               C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, c_i32p, c_f32p, c_i32p, c_i32p,
                                c_i32p, C.c_void_p]),
+    "lemon_split_cast": (C.c_int, [C.c_void_p, c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p]),
     "lemon_knn_exact": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_i32p, c_i32p, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_int, C.c_int, C.c_int, c_f32p, c_i32p, C.c_void_p]),
     "lemon_score": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p,

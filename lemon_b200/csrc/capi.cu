@@ -38,14 +38,13 @@ extern "C" int lemon_ctx_create(int device, lemon_ctx** out) {
   c->tc_scratch = nullptr;
   c->tc_scratch_bytes = 0;
   c->encode_tiled = nullptr;
-  c->tune_kres = c->tune_debug = c->tune_cert = c->tune_boot = c->tune_bn = c->tune_stagger = c->tune_variant = -1;
+  c->tune_kres = c->tune_debug = c->tune_cert = c->tune_boot = c->tune_bn = -1;
 #ifdef LEMON_TC_EXPERIMENT
   {
     auto env_int = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : -1; };
     c->tune_kres = env_int("LEMON_TC_KRES");       c->tune_debug = env_int("LEMON_TC_DEBUG");
     c->tune_cert = env_int("LEMON_TC_CERT");       c->tune_boot = env_int("LEMON_TC_BOOT");
-    c->tune_bn = env_int("LEMON_TC_BN");           c->tune_stagger = env_int("LEMON_TC_STAGGER");
-    c->tune_variant = env_int("LEMON_TC_VARIANT");
+    c->tune_bn = env_int("LEMON_TC_BN");
   }
 #endif
   *out = c;

@@ -50,6 +50,45 @@ normalize_cast_kernel(const float* __restrict__ in, float* __restrict__ out_f32,
   }
 }
 
+// Split-precision operands for the second tensor-core pass (rows the first pass could not certify).
+//   x = x_hi + x_lo + x_e,  x_hi = fp16(x),  x_lo = fp16(x - x_hi)   (x_lo may be an fp16 subnormal: its absolute
+//   rounding error is <= 2^-25 per component, so ||x_e|| ~ 2^-22 ||x|| instead of the 2^-11 ||x|| of one fp16 word)
+// Queries are laid out [hi | hi | lo], database rows [hi | lo | hi] (each block d16 wide), so that ONE K-loop of the
+// unchanged K1 kernel over 3*d16 columns accumulates  q_hi.b_hi + q_hi.b_lo + q_lo.b_hi  in fp32.
+// row_stats / stats_max are written in the layout lemon_rerank reads, with the residual ||x_e|| in the place of the
+// one-word rounding error:  {||x||, ||x||, ||x_e||, ||x||^2}  and maxima  {||x||, ||x||, ||x_e||, | ||x||^2 - 1 |}.
+__global__ void __launch_bounds__(256)
+split_cast_kernel(const float* __restrict__ x, __half* __restrict__ out, float* __restrict__ row_stats,
+                  float* __restrict__ stats_max, int64_t n, int d, int d16, int role) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  float m0 = 0.f, m2 = 0.f, m3 = 0.f;
+  for (int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const float* xr = x + row * d;
+    __half* o = out + row * (3 * int64_t(d16));
+    float sx = 0.f, se = 0.f;
+    for (int c = lane; c < d16; c += 32) {
+      const float v = c < d ? xr[c] : 0.f;
+      const __half hi = __float2half_rn(v);
+      const float r1 = v - __half2float(hi);            // exact in fp32
+      const __half lo = __float2half_rn(r1);
+      const float e = r1 - __half2float(lo);            // exact in fp32
+      sx = fmaf(v, v, sx); se = fmaf(e, e, se);
+      o[c] = hi;
+      o[d16 + c] = role == 0 ? hi : lo;
+      o[2 * d16 + c] = role == 0 ? lo : hi;
+    }
+    sx = warp_sum(sx); se = warp_sum(se);
+    const float nx = sqrtf(sx), ne = sqrtf(se);
+    if (lane == 0 && row_stats) reinterpret_cast<float4*>(row_stats)[row] = make_float4(nx, nx, ne, sx);
+    m0 = fmaxf(m0, nx); m2 = fmaxf(m2, ne); m3 = fmaxf(m3, fabsf(sx - 1.0f));
+  }
+  if (stats_max && lane == 0) {
+    atomic_max_pos(stats_max + 0, m0); atomic_max_pos(stats_max + 1, m0);
+    atomic_max_pos(stats_max + 2, m2); atomic_max_pos(stats_max + 3, m3);
+  }
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(256)
 rowwise_dist_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
@@ -99,6 +138,23 @@ extern "C" int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b
     lemon::rowwise_dist_kernel<LEMON_METRIC_IP><<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, d);
   else
     lemon::rowwise_dist_kernel<LEMON_METRIC_L2><<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(a, b, out, n, d);
+  ctx->launches++;
+  LEMON_CUDA_CHECK(ctx, cudaGetLastError());
+  return LEMON_OK;
+}
+
+extern "C" int lemon_split_cast(lemon_ctx* ctx, const float* x, void* out_f16, float* row_stats, float* stats_max,
+                                int64_t n, int d, int d16, int role, void* stream) {
+  if (!ctx) return LEMON_ERR_INVALID;
+  if (!x || !out_f16 || n < 0 || d <= 0 || d16 < d || d16 % 64 || (role != 0 && role != 1))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "split_cast: bad args");
+  if (stats_max) LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(stats_max, 0, 4 * sizeof(float), (cudaStream_t)stream));
+  if (n == 0) return LEMON_OK;
+  int64_t blocks = (n + 7) / 8;
+  const int64_t cap = int64_t(ctx->num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  lemon::split_cast_kernel<<<unsigned(blocks), 256, 0, (cudaStream_t)stream>>>(x, (__half*)out_f16, row_stats, stats_max, n, d,
+                                                                             d16, role);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());
   return LEMON_OK;

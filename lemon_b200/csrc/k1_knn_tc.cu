@@ -48,8 +48,7 @@ struct TcParams {
   float* cand_theta;    // [nq_pad][nseg][2]: every column not in the list has approximate value <= theta
   int cert;             // ladder: exceedance count that certifies a level (`keep` of the C ABI)
   int boot_tiles;       // 256-column tiles per item that only bootstrap the thresholds (8 or 16; 0 = off)
-  int debug;            // experiments (LEMON_TC_EXPERIMENT builds): 1 = epilogue does no work, 2 = filter only
-  int stagger;          // CTA pair u starts its DB walk (u % stagger) tiles in (wraps around); <= 8
+  int debug;            // experiments (-DLEMON_TC_EXPERIMENT builds): 1 = epilogue does no work, 2 = filter only
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -215,8 +214,6 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // ---------------------------------------------------------------- streaming top-k (epilogue)
 constexpr int kBootTiles = 8;                  // 256-column tiles per item (4 per epilogue group) that bootstrap the row thresholds
 constexpr int kBootMinTiles = 16;              // items shorter than this run without the bootstrap (their lists fill up once and are reduced exactly)
-constexpr int kDefaultStagger = 0;             // see tile_offset()
-constexpr int kDefaultVariant = 0;             // TcParams::variant
 constexpr int kEpiGroups = 2;                  // epilogue warp groups; group g scans column half g of every accumulator tile
 
 // Merge of two descending-sorted 64-key lists into the best 64, descending.  Lanes 0-7 hold list A
@@ -430,19 +427,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Staggered DB walk: all CTA pairs stream the same DB, and in lockstep they all ask the same few L2 slices for the
-// same 16 KB at the same moment.  Pair u starts (u % stagger) tiles into its segment and wraps around, so at any
-// time the pairs read a window of `stagger` consecutive tiles (still L2-resident: the leaders fetch a tile from DRAM
-// once).  The offset stays below 8 tiles so that the bootstrap tiles (the first 8 of the walk) never include the
-// segment's partial last tile (items with a bootstrap have >= 16 tiles).
-__device__ __forceinline__ int64_t tile_offset(const TcParams& p, int64_t unit, int64_t ntiles) {
-  if (p.stagger <= 1) return 0;
-  const int64_t o = unit % p.stagger;
-  return o < ntiles ? o : o % ntiles;
-}
-
 // ------------------------------------------------------------------------------------ kernel
-template <int CG, int BN, int VAR>
+template <int CG, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_db, const TcParams p) {
   extern __shared__ unsigned char smem_raw[];
@@ -506,10 +492,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int kc = 0; kc < p.kres; ++kc)
           tma_load_2d<CG>(a_smem + kc * kAChunkBytes, &map_q, afull_l, kc * kBK, row0);
         const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);   // bootstrap tiles are scanned twice
-        const int64_t t_off = tile_offset(p, unit, ntiles);
         for (int64_t i = 0; i < nsteps; ++i) {
-          int64_t t = (i < ntiles ? i : i - ntiles) + t_off;
-          if (t >= ntiles) t -= ntiles;
+          const int64_t t = i < ntiles ? i : i - ntiles;
           const int dbrow = int(col0 + t * BN + cta_rank * kBRows);
           for (int kc = 0; kc < p.kchunks; ++kc) {
             if (kc >= p.kres) {   // non-resident query chunk: one ring stage (same size as a DB stage)
@@ -613,10 +597,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const int nboot = ntiles >= kBootMinTiles ? kBoot : 0;
       const int64_t nsteps = ntiles + nboot;
       int bcount = 0;
-      const int64_t t_off = tile_offset(p, unit, ntiles);
       for (int64_t i = 0; i < nsteps; ++i, ++tc) {
-        int64_t t = (i < ntiles ? i : i - ntiles) + t_off;
-        if (t >= ntiles) t -= ntiles;
+        const int64_t t = i < ntiles ? i : i - ntiles;
         const uint32_t buf = tc % kNBuf, use = tc / kNBuf;
         LEMON_PROF(const long long pf_a = clock64();)
         mbar_wait(tmem_full + 8 * buf, use & 1);
@@ -667,7 +649,12 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         if (!(p.debug & 1)) {
           const int nchunks = (valid + 31) >> 5;
           const bool partial = valid < kGrpCols;     // only the last tile of a segment
-          auto scan_chunk = [&](uint32_t (&r)[32], const int c) {
+#pragma unroll 1
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int c = ch * 32;
+            uint32_t r[32];
+            tmem_ld32_async(taddr + c, r);
+            tmem_wait_ld(r);
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -692,47 +679,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
                 if (__any_sync(kFull, gm[g] > theta)) {
-                  if (VAR & 1) {
-                    // a group with a survivor in some lane holds ~1.3 surviving (row, column) pairs on average: one
-                    // vote per column and an append only for the columns that have one (3 instead of 8 instructions
-                    // for each of the other columns)
 #pragma unroll
-                    for (int j = 8 * g; j < 8 * g + 8; ++j)
-                      if (__any_sync(kFull, v[j] > theta)) append_if_above(wp, v[j], theta, nidx0 - uint32_t(j));
-                  } else {
-#pragma unroll
-                    for (int j = 8 * g; j < 8 * g + 8; ++j) append_if_above(wp, v[j], theta, nidx0 - uint32_t(j));
-                  }
+                  for (int j = 8 * g; j < 8 * g + 8; ++j) append_if_above(wp, v[j], theta, nidx0 - uint32_t(j));
                 }
               }
               cnt = int((uint32_t(wp) - keys_lo) >> 3);
             }
             __syncwarp();
             if (__any_sync(kFull, cnt > kListCap - 32)) prune_full_rows(warp_keys, row_stride, cnt, theta, ld, p.cert, lane);   // must not overflow
-          };
-          if (VAR & 2) {
-            // double-buffered TMEM reads: the load of chunk c+1 is in flight while chunk c is scanned
-            uint32_t ra[32], rb[32];
-            tmem_ld32_async(taddr, ra);
-#pragma unroll 1
-            for (int ch = 0; ch < nchunks; ch += 2) {
-              tmem_wait_ld(ra);
-              if (ch + 1 < nchunks) tmem_ld32_async(taddr + (ch + 1) * 32, rb);
-              scan_chunk(ra, ch * 32);
-              if (ch + 1 < nchunks) {
-                tmem_wait_ld(rb);
-                if (ch + 2 < nchunks) tmem_ld32_async(taddr + (ch + 2) * 32, ra);
-                scan_chunk(rb, (ch + 1) * 32);
-              }
-            }
-          } else {
-#pragma unroll 1
-            for (int ch = 0; ch < nchunks; ++ch) {
-              uint32_t r[32];
-              tmem_ld32_async(taddr + ch * 32, r);
-              tmem_wait_ld(r);
-              scan_chunk(r, ch * 32);
-            }
           }
         }
         LEMON_PROF({ const long long pf_c = clock64() - pf_b; pf_scan += pf_c; if (pf_c > pf_max) pf_max = pf_c; })
@@ -795,8 +749,7 @@ static int make_map(lemon_ctx* ctx, CUtensorMap* map, const void* base, int64_t 
   return LEMON_OK;
 }
 
-// VAR (epilogue variant): bit 0 = per-column votes inside a surviving 8-column group, bit 1 = double-buffered tcgen05.ld
-template <int CG, int BN, int VAR>
+template <int CG, int BN>
 static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t nq, int64_t m, int d16, int nseg, int keep,
                      uint64_t* cand_keys, int32_t* cand_cnt, float* cand_theta, cudaStream_t stream) {
   const int kchunks = d16 / kBK;
@@ -828,10 +781,10 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const int64_t row_tiles = (nq + kBM * CG - 1) / (kBM * CG);
   p.n_items = row_tiles * nseg;
   p.cand_keys = cand_keys; p.cand_cnt = cand_cnt; p.cand_theta = cand_theta;
+  // tuning knobs: library defaults unless the ctx was created by a -DLEMON_TC_EXPERIMENT build (capi.cu)
   p.debug = ctx->tune_debug > 0 ? ctx->tune_debug : 0;
   p.cert = (ctx->tune_cert >= 16 && ctx->tune_cert <= kKeep) ? ctx->tune_cert : keep;
   p.boot_tiles = (ctx->tune_boot == 0 || ctx->tune_boot == 8 || ctx->tune_boot == 16) ? ctx->tune_boot : kBootTiles;
-  p.stagger = ctx->tune_stagger >= 0 ? (ctx->tune_stagger > 8 ? 8 : ctx->tune_stagger) : kDefaultStagger;
 
   int64_t units = ctx->num_sms / CG;
   if (units > p.n_items) units = p.n_items;
@@ -842,7 +795,7 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   rc = make_map(ctx, &map_db, db16, m, d16, BN / CG);
   if (rc) return rc;
 
-  auto kern = knn_tc_kernel<CG, BN, VAR>;
+  auto kern = knn_tc_kernel<CG, BN>;
   LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
@@ -865,35 +818,24 @@ extern "C" int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void*
                                     float* cand_theta, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
-  if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D_TC ||
+  if (!q16 || !db16 || !cand_keys || !cand_cnt || !cand_theta || nq < 0 || m < 1 || d16 < 64 || d16 % 64 || d16 > LEMON_MAX_D16_OPERAND ||
       nseg < 1 || nseg > 64 || keep < 0 || (keep > 0 && keep < 16) || keep > kKeep || m >= (int64_t(1) << 31) || (uintptr_t(q16) & 15) || (uintptr_t(db16) & 15) ||
       (uintptr_t(cand_keys) & (kListCap * 8 - 1)))
-    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 8 KB-aligned cand_keys)", LEMON_MAX_D_TC);
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: bad args (d16 %% 64 == 0, d16 <= %d, 16B-aligned operands, 8 KB-aligned cand_keys)", LEMON_MAX_D16_OPERAND);
   if (nq == 0) return LEMON_OK;
   if (keep == 0) keep = kKeep;
   if (cta_group == 0) cta_group = 2;   // CTA pairs: half the SMEM/L2 operand traffic per MMA
   cudaStream_t st = (cudaStream_t)stream;
   LEMON_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
   int bn = ctx->tune_bn > 0 ? ctx->tune_bn : 0;      // experiments: force the DB tile width (128 or 256)
-#define LEMON_TC_ARGS ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st
   if (cta_group == 1) {
     if (bn == 0) bn = d16 <= 512 ? 256 : 128;
-    if (bn == 256 && d16 <= 512) return launch_tc<1, 256, kDefaultVariant>(LEMON_TC_ARGS);
-    return launch_tc<1, 128, kDefaultVariant>(LEMON_TC_ARGS);
+    if (bn == 256 && d16 <= 512) return launch_tc<1, 256>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<1, 128>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
   }
   if (cta_group == 2) {
-    if (bn == 128) return launch_tc<2, 128, kDefaultVariant>(LEMON_TC_ARGS);
-#ifdef LEMON_TC_EXPERIMENT
-    switch (ctx->tune_variant) {
-      case 0: return launch_tc<2, 256, 0>(LEMON_TC_ARGS);
-      case 1: return launch_tc<2, 256, 1>(LEMON_TC_ARGS);
-      case 2: return launch_tc<2, 256, 2>(LEMON_TC_ARGS);
-      case 3: return launch_tc<2, 256, 3>(LEMON_TC_ARGS);
-      default: break;
-    }
-#endif
-    return launch_tc<2, 256, kDefaultVariant>(LEMON_TC_ARGS);
+    if (bn == 128) return launch_tc<2, 128>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
+    return launch_tc<2, 256>(ctx, q16, db16, nq, m, d16, nseg, keep, cand_keys, cand_cnt, cand_theta, st);
   }
-#undef LEMON_TC_ARGS
   return lemon_set_error(ctx, LEMON_ERR_INVALID, "knn_candidates: cta_group must be 0, 1 or 2");
 }

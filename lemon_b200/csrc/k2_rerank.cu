@@ -31,8 +31,8 @@ __global__ void __launch_bounds__(kRrWarps * 32)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const uint64_t* __restrict__ cand_keys,
               const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_theta,
               const float* __restrict__ q_row_stats, const float* __restrict__ db_stats_max, float acc_eps, int64_t nq,
-              int64_t m, int d, int nlist, int kp, float* __restrict__ top_val, int32_t* __restrict__ top_idx,
-              int32_t* __restrict__ uncert_rows, int32_t* __restrict__ n_uncert) {
+              int64_t m, int d, int nlist, int kp, const int32_t* __restrict__ out_rows, float* __restrict__ top_val,
+              int32_t* __restrict__ top_idx, int32_t* __restrict__ uncert_rows, int32_t* __restrict__ n_uncert) {
   // per warp: selection buffer (kSelCap keys: all candidates above the bound that may still be in the top-kp) and
   // the exact keys of the gathered candidates (kCap)
   extern __shared__ __align__(16) unsigned char rr_smem[];
@@ -152,7 +152,8 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
 #pragma unroll
     for (int i = 0; i < 8; ++i) { const int e = lane * 8 + i; key[i] = e < ecnt ? ebuf[e] : 0ull; }
     warp_sort256_desc(key, lane);
-    // ---- 3. emit the exact top list
+    // ---- 3. emit the exact top list (second-pass calls: query row r is row out_rows[r] of the caller's lists)
+    const int64_t orow = out_rows ? int64_t(out_rows[row]) : row;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int e = lane * 8 + i;
@@ -160,8 +161,8 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
         const bool ok = key[i] != 0ull;
         float v = ok ? key_val(key[i]) : -CUDART_INF_F;
         if (METRIC == LEMON_METRIC_L2) v = -v;
-        top_val[row * kp + e] = v;
-        top_idx[row * kp + e] = ok ? key_idx(key[i]) : -1;
+        top_val[orow * kp + e] = v;
+        top_idx[orow * kp + e] = ok ? key_idx(key[i]) : -1;
       }
     }
     // ---- 4. certificate: every column outside the lists has approximate ip <= B, hence exact ip <= B + eps
@@ -176,7 +177,7 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
       const bool certified = !overflow && kth_key != 0ull && key_val(kth_key) > T;
       if (!certified) {
         const int pos = atomicAdd(n_uncert, 1);
-        uncert_rows[pos] = int32_t(row);
+        uncert_rows[pos] = int32_t(orow);
       }
     }
     __syncwarp();
@@ -188,8 +189,8 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
 extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, const uint64_t* cand_keys,
                             const int32_t* cand_cnt, const float* cand_theta, const float* q_row_stats,
                             const float* db_stats_max, float acc_eps, int64_t nq, int64_t m, int d, int nlist, int kp,
-                            int metric, float* top_val, int32_t* top_idx, int32_t* uncert_rows, int32_t* n_uncert,
-                            void* stream) {
+                            int metric, const int32_t* out_rows, float* top_val, int32_t* top_idx, int32_t* uncert_rows,
+                            int32_t* n_uncert, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!q || !db || !cand_keys || !cand_cnt || !cand_theta || !top_val || !top_idx || !uncert_rows || !n_uncert || nq < 0 ||
@@ -205,11 +206,11 @@ extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, con
   LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(rerank_kernel<LEMON_METRIC_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (metric == LEMON_METRIC_IP)
     rerank_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kRrWarps * 32, smem, (cudaStream_t)stream>>>(
-        q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, top_val, top_idx,
+        q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, out_rows, top_val, top_idx,
         uncert_rows, n_uncert);
   else
     rerank_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kRrWarps * 32, smem, (cudaStream_t)stream>>>(
-        q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, top_val, top_idx,
+        q, db, cand_keys, cand_cnt, cand_theta, q_row_stats, db_stats_max, acc_eps, nq, m, d, nlist, kp, out_rows, top_val, top_idx,
         uncert_rows, n_uncert);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());

@@ -19,7 +19,7 @@ struct lemon_ctx {
   void* encode_tiled;   // cuTensorMapEncodeTiled, resolved lazily
   // K1 tuning knobs; -1 = library default.  Only builds with -DLEMON_TC_EXPERIMENT read them from the environment
   // (once, at ctx creation); the product build always runs the defaults.
-  int tune_kres, tune_debug, tune_cert, tune_boot, tune_bn, tune_stagger, tune_variant;
+  int tune_kres, tune_debug, tune_cert, tune_boot, tune_bn;
 };
 
 int lemon_set_error(lemon_ctx* ctx, int code, const char* fmt, ...);

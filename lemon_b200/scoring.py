@@ -124,7 +124,7 @@ def count_uncertified(info: dict) -> "int | None":
     c = info.get("n_uncertified")
     if c is None:
         return None
-    return int(sum(int(t.item()) for t in (c if isinstance(c, (list, tuple)) else [c])))
+    return int(sum(int(t.item()) if torch.is_tensor(t) else int(t) for t in (c if isinstance(c, (list, tuple)) else [c])))
 
 
 def tc_keep(kp: int) -> int:
@@ -223,8 +223,17 @@ class LemonScorer:
         self.dedup = dedup
         self.num_sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.db = None
+        self._pin, self._pin_next = None, 0
+        self.second_pass_enabled = True      # split-precision tensor-core pass for uncertified rows (tests switch it off)
         self.last_info: dict = {}
         self.k1_events: list | None = None
+
+    def _pinned_slot(self) -> torch.Tensor:
+        """One int32 of pinned host memory for an asynchronous counter read-back (a small ring, allocated once)."""
+        if self._pin is None:
+            self._pin = torch.empty(256, dtype=torch.int32).pin_memory()
+        self._pin_next = (self._pin_next + 1) % 256
+        return self._pin[self._pin_next:self._pin_next + 1]
 
     # ------------------------------------------------------------------ K0
     def prepare(self, x, normalize: bool = True, need_f16: bool = True) -> Prepared:
@@ -367,8 +376,10 @@ class LemonScorer:
             self.k1_events.append((ev[0], ev[1], 2.0 * q.n * db.n * db.d))
         return cand_keys, cand_cnt, cand_theta, nseg
 
-    def rerank(self, q: Prepared, db: Prepared, cand, kp: int, metric: int, use_bound: bool = True, out=None):
-        """K2a on the output of knn_candidates (`cand` = its first three return values)."""
+    def rerank(self, q: Prepared, db: Prepared, cand, kp: int, metric: int, use_bound: bool = True, out=None,
+               out_rows=None, acc_coef: float | None = None):
+        """K2a on the output of knn_candidates (`cand` = its first three return values).  out_rows (int32 [q.n]):
+        query row r belongs to row out_rows[r] of `out` (second pass on a gathered subset)."""
         cand_keys, cand_cnt, cand_theta = cand
         if out is None:
             out = (torch.empty((q.n, kp), dtype=torch.float32, device=self.device),
@@ -376,13 +387,52 @@ class LemonScorer:
         top_val, top_idx = out
         uncert = torch.empty(max(q.n, 1), dtype=torch.int32, device=self.device)
         n_unc = torch.empty(1, dtype=torch.int32, device=self.device)           # zeroed by the library call
+        acc = acc_eps_coef(db.d16, db.d) if acc_coef is None else acc_coef
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_rerank(
                 self.ctx.handle, _ptr(q.f32), _ptr(db.f32), _ptr(cand_keys), _ptr(cand_cnt), _ptr(cand_theta),
                 _ptr(q.row_stats) if use_bound else None, _ptr(db.stats_max) if use_bound else None,
-                C.c_float(acc_eps_coef(db.d16, db.d)), q.n, db.n, db.d, cand_cnt.shape[1], kp, metric, _ptr(top_val), _ptr(top_idx),
+                C.c_float(acc), q.n, db.n, db.d, cand_cnt.shape[1], kp, metric, _ptr(out_rows), _ptr(top_val), _ptr(top_idx),
                 _ptr(uncert), _ptr(n_unc), _stream()), "lemon_rerank")
         return top_val, top_idx, uncert, n_unc
+
+    # ------------------------------------------------ second tensor-core pass (split precision)
+    def split_operands(self, p: Prepared, role: int) -> Prepared:
+        """[hi | hi | lo] (role 0, queries) / [hi | lo | hi] (role 1, database) fp16 operands of 3*d16 columns and the
+        statistics of the residual (include/lemon_b200.h: lemon_split_cast)."""
+        d16 = p.d16
+        out16 = torch.empty((p.n, 3 * d16), dtype=torch.float16, device=self.device)
+        row_stats = torch.empty((p.n, 4), dtype=torch.float32, device=self.device)
+        stats_max = torch.empty(4, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_split_cast(self.ctx.handle, _ptr(p.f32), _ptr(out16), _ptr(row_stats), _ptr(stats_max),
+                                                     p.n, p.d, d16, role, _stream()), "lemon_split_cast")
+        return Prepared(p.f32, out16, row_stats, stats_max, p.n, p.d, 3 * d16)
+
+    def second_pass(self, q: Prepared, db: Prepared, rows: torch.Tensor, kp: int, metric: int, out):
+        """Rows the first pass could not certify (their fp16 rounding bound ~6e-4 exceeds the gap below the kp-th
+        neighbour) are searched again with split-precision operands (three fp16 products per pair, bound ~1e-4 at
+        d = 768) and keep = 64 candidates per list, before anything is sent to the fp32 brute-force kernel (two orders
+        of magnitude slower per row).  `rows`: int32 ids of the rows of q; their lists in `out` are overwritten.
+        Returns (uncert, n_unc) of the rows that are still uncertified (ids of rows of q)."""
+        n2 = rows.numel()
+        dev = self.device
+
+        def gather(src, cols, dtype):
+            dst = torch.empty((n2, cols), dtype=dtype, device=dev)
+            with torch.cuda.device(dev):
+                self.ctx.check(self.lib.lemon_gather_rows(self.ctx.handle, _ptr(src), _ptr(rows), None, n2,
+                                                          cols * src.element_size(), _ptr(dst), _stream()), "lemon_gather_rows")
+            return dst
+        q2 = Prepared(gather(q.f32, q.d, torch.float32), None, None, None, n2, q.d, q.d16)
+        q2s = self.split_operands(q2, 0)
+        dbs = getattr(db, "_split", None)
+        if dbs is None:
+            dbs = db._split = self.split_operands(db, 1)         # built on first use, kept with the staged database
+        *cand, _ = self.knn_candidates(q2s, dbs, keep=MAX_KP)
+        _, _, uncert, n_unc = self.rerank(q2s, dbs, cand, kp, metric, out=out, out_rows=rows,
+                                          acc_coef=acc_eps_coef(dbs.d16, db.d) + 2.0 ** -21)     # + the q_lo.b_lo term
+        return uncert, n_unc
 
     def knn(self, q: Prepared, db: Prepared, kp: int, metric: int, mode: str | None = None):
         """Exact top-kp lists [nq,kp] (fp32 values, int32 DB rows), total order (best value, lower index).
@@ -414,19 +464,38 @@ class LemonScorer:
         top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
         cg = self.cta_group if self.cta_group else 2
         parts = plan_parts(q.n, db.n, self.num_sms, cg)
-        n_uncs, nsegs = [], []
+        pending, nsegs = [], []
         for r0, r1, ns in parts:
             qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)
             *cand, nseg = self.knn_candidates(qs, db, nseg=ns, keep=tc_keep(kp))
             tv, ti = top_val[r0:r1], top_idx[r0:r1]
             _, _, uncert, n_unc = self.rerank(qs, db, cand, kp, metric, out=(tv, ti))
-            # uncertified rows: exact fp32 brute force on the GPU; the kernel reads the row count on the
-            # device, so no host synchronisation is needed here
-            self.knn_exact(qs, db, kp, metric, top=(tv, ti), rows=uncert, n_rows=n_unc)
-            n_uncs.append(n_unc)
+            host = self._pinned_slot()
+            host.copy_(n_unc, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((qs, tv, ti, uncert, n_unc, host, ev))
             nsegs.append(nseg)
+        # Rows without a certificate.  Their count is read back once per launch (all launches are queued by now, so
+        # the host only waits for work that has to finish anyway): it sizes the second tensor-core pass.
+        first, second = [], []
+        for qs, tv, ti, uncert, n_unc, host, ev in pending:
+            ev.synchronize()
+            n1 = int(host[0])
+            first.append(n1)
+            if n1 == 0:
+                second.append(0)
+                continue
+            if self.second_pass_enabled and db.d16 * 3 <= MAX_D_TC * 3:
+                uncert, n_unc = self.second_pass(qs, db, uncert[:n1], kp, metric, (tv, ti))
+                second.append(n_unc)
+            else:
+                second.append(n1)
+            # what is still uncertified: exact fp32 brute force on the GPU (row list and count stay on the device)
+            self.knn_exact(qs, db, kp, metric, top=(tv, ti), rows=uncert, n_rows=n_unc)
         self.last_info = {"path": "tc", "nseg": nsegs[0] if len(nsegs) == 1 else nsegs,
-                          "n_uncertified": n_uncs}      # device counters, one per launch (sum them after a sync)
+                          "n_uncertified_first_pass": int(sum(first)),
+                          "n_uncertified": second}      # after the second pass: ints (0) or device counters, one per launch
         return top_val, top_idx
 
     # ------------------------------------------------- run_lemon.py:163-176

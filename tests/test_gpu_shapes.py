@@ -203,3 +203,76 @@ def test_keep_lowest_matches_sorted_order(lb, n, keep):
     assert (s[got][differ] == 0.0).all() if differ.any() else True
     ids = lb.filter_lowest_scores(torch.from_numpy(s), min(keep, 100), idx=np.arange(n) * 2 + 1)
     assert (ids.cpu().numpy() == got[:100] * 2 + 1).all()
+
+
+def _narrow_cone(n, d, shared, seed, dev):
+    """CLIP-like 'cone' geometry: every embedding shares a large common component, which compresses all similarities
+    (and the gaps between neighbours) by 1 - shared: the distribution on which an fp16 first pass loses certificates."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+    c0 = torch.nn.functional.normalize(torch.randn(1, d, generator=g, device=dev), dim=1)
+    z = torch.nn.functional.normalize(torch.randn(n, d, generator=g, device=dev), dim=1)
+    return torch.nn.functional.normalize(shared ** 0.5 * c0 + (1 - shared) ** 0.5 * z, dim=1).contiguous()
+
+
+def test_split_precision_bound_is_rigorous(lb):
+    """|q_hi.b_hi + q_hi.b_lo + q_lo.b_hi (fp32 TMEM accumulation) - float64 inner product| <= the bound the second
+    pass certifies with, and that bound is ~an order of magnitude below the one-word fp16 bound."""
+    import torch
+    from lemon_b200.scoring import acc_eps_coef, decode_candidates
+    dev = torch.device("cuda", 0)
+    x = _narrow_cone(20_000, 768, 0.5, 3, dev)
+    sc = lb.get_scorer(0)
+    dbp = sc.prepare(x, True)
+    qp = lemon_slice(dbp, 0, 1024)
+    qs, dbs = sc.split_operands(qp, 0), sc.split_operands(dbp, 1)
+    assert qs.f16.shape == (1024, 3 * 768) and dbs.d16 == 2304
+    ck, cc, ct, _ = sc.knn_candidates(qs, dbs, nseg=1, keep=64)
+    cv, ci = decode_candidates(ck, cc, 1024)
+    cv, ci = cv[:, :64].astype(np.float64), ci[:, :64]
+    assert (ci >= 0).all()
+    q64, db64 = qp.f32.cpu().numpy().astype(np.float64), dbp.f32.cpu().numpy().astype(np.float64)
+    exact = np.einsum("nd,nkd->nk", q64, db64[ci])
+    rs, smax = qs.row_stats.cpu().numpy(), dbs.stats_max.cpu().numpy()
+    acc = acc_eps_coef(2304, 768) + 2.0 ** -21
+    eps2 = rs[:, 2] * smax[1] + rs[:, 0] * smax[2] + acc * np.maximum(rs[:, 0], rs[:, 1]) * max(smax[0], smax[1])
+    err = np.abs(cv - exact).max(axis=1)
+    assert (err <= eps2).all(), (err.max(), eps2.min())
+    rs1, smax1 = qp.row_stats.cpu().numpy(), dbp.stats_max.cpu().numpy()
+    eps1 = rs1[:, 2] * smax1[1] + rs1[:, 0] * smax1[2] + acc_eps_coef(768, 768) * rs1[:, 0] * smax1[0]
+    assert np.median(eps2) < 0.6 * np.median(eps1)
+    print("eps first pass %.2e, second pass %.2e, worst observed error %.2e" % (np.median(eps1), np.median(eps2), err.max()))
+
+
+def lemon_slice(p, a, b):
+    from lemon_b200.scoring import _slice_prepared
+    return _slice_prepared(p, a, b)
+
+
+def test_second_pass_rescues_rows_the_fp16_pass_cannot_certify(lb):
+    """Narrow-cone embeddings: a large share of the rows fails the first-pass certificate; the split-precision second
+    pass certifies (nearly) all of them, so (nearly) nothing reaches the fp32 brute-force kernel, and the lists are
+    BITWISE those of the exact kernel."""
+    import torch
+    from lemon_b200.scoring import count_uncertified
+    dev = torch.device("cuda", 0)
+    n, d, kp = 100_000, 512, 31
+    x = _narrow_cone(n, d, 0.85, 11, dev)
+    sc = lb.get_scorer(0)
+    dbp = sc.prepare(x, True)
+    qp = lemon_slice(dbp, 0, 8192)
+    tv, ti = sc.knn(qp, dbp, kp, 0, mode="tc")
+    info = dict(sc.last_info)
+    first, left = info["n_uncertified_first_pass"], count_uncertified(info)
+    print("first pass uncertified %d of 8192, after the second pass %d" % (first, left))
+    assert first > 400                      # the distribution is hard for one fp16 word ...
+    assert left <= first // 20              # ... and easy for the split-precision pass
+    ev, ei = sc.knn(lemon_slice(dbp, 0, 2048), dbp, kp, 0, mode="exact")
+    assert (ti[:2048] == ei).all() and (tv[:2048] == ev).all()
+    # with the second pass switched off the same rows go to the exact kernel: same lists
+    sc.second_pass_enabled = False
+    try:
+        tv0, ti0 = sc.knn(lemon_slice(dbp, 0, 2048), dbp, kp, 0, mode="tc")
+    finally:
+        sc.second_pass_enabled = True
+    assert (ti0 == ei).all() and (tv0 == ev).all()

@@ -187,6 +187,12 @@ int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_
  *   ascending row index (the documented total order).
  * lemon_hash_rows: the 63-bit row hash alone (diagnostics / tests).
  */
+/* lemon_dedup_count: counters[0] = number of rows whose 63-bit hash equals an earlier row's (n - counters[0] =
+ * number of unique rows, barring hash collisions): two kernels, enough to decide whether lemon_dedup_build is
+ * worth running.  workspace: lemon_dedup_count_workspace_bytes(n) bytes, 256 B aligned. */
+int64_t lemon_dedup_count_workspace_bytes(int64_t n);
+int lemon_dedup_count(lemon_ctx* ctx, const float* x, int64_t n, int d, void* workspace, int32_t* counters,
+                      void* stream);
 int64_t lemon_dedup_workspace_bytes(int64_t n);
 int lemon_dedup_build(lemon_ctx* ctx, const float* x, int64_t n, int d, void* workspace, int32_t* rep_rows,
                       int32_t* members, int64_t* offsets, int32_t* counters, void* stream);

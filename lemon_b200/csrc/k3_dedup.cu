@@ -1,11 +1,12 @@
 // Exact-duplicate handling for the kNN database, entirely on the device.  Classification datasets have only C
 // distinct text embeddings (run_lemon.py:117-119,140-143) and caption-noise injection duplicates captions
 // (lib/datasets/noise_captioning.py:44-53), so thousands of DB rows can be bit-identical.  Identical rows are
-// searched once:
+// searched once.  Step 1 (every database): hash_rows -> count_dups (open-addressing table) gives the number of
+// duplicate rows in two kernels; the host reads that one counter (the number of unique rows sizes the search
+// operands, so one round trip per database is inherent).  Step 2 (only databases with >= 10 % duplicates):
 //   hash_rows -> LSD radix sort of (hash, row) -> run flags -> scans -> bit-wise verification against the run's
 //   first (= lowest) row -> groups renumbered by ascending representative row -> offsets / members
-// all queued on one stream without a host round trip (the host reads back two counters once: the number of
-// unique rows sizes the search operands).  The search then runs on one representative per group and
+// all queued on one stream.  The search then runs on one representative per group and
 // expand_groups turns every hit into its members in ascending DB index — the list the full search returns under
 // the documented total order (value best-first, then index ascending).
 //
@@ -39,6 +40,27 @@ hash_rows_kernel(const uint32_t* __restrict__ x, int64_t n, int d, uint64_t* __r
       if (vals) vals[row] = int32_t(row);
     }
   }
+}
+
+// Counts the rows whose 63-bit hash was already seen (open-addressing table, one atomicCAS per probe): n - count is
+// the number of distinct hashes, i.e. the number of unique rows unless two different rows collide.  This is all the
+// caller needs to decide whether the database is worth de-duplicating; the sort below only runs when it is.
+__global__ void __launch_bounds__(256)
+count_dups_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ table, uint64_t mask,
+                  int32_t* __restrict__ counters) {
+  int local = 0;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const unsigned long long tag = keys[i] | 0x8000000000000000ull;       // never 0 (= empty slot)
+    uint64_t slot = (keys[i] * 0x9e3779b97f4a7c15ull) >> 20 & mask;
+    for (uint64_t probes = 0; probes <= mask; ++probes) {
+      const unsigned long long prev = atomicCAS(table + slot, 0ull, tag);
+      if (prev == 0ull) break;
+      if (prev == tag) { ++local; break; }
+      slot = (slot + 1) & mask;
+    }
+  }
+  local = __reduce_add_sync(kFull, local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(counters, local);
 }
 
 // ------------------------------------------------------------------------------------ radix sort
@@ -353,6 +375,39 @@ static inline SortWs carve_sort_ws(void* ws, int64_t n) {
 }
 
 }  // namespace lemon
+
+static inline uint64_t dup_table_slots(int64_t n) {
+  uint64_t s = 1024;
+  while (s < uint64_t(n) * 2) s <<= 1;
+  return s;
+}
+
+extern "C" int64_t lemon_dedup_count_workspace_bytes(int64_t n) {
+  return n < 1 ? 0 : int64_t(lemon::align256(size_t(n) * 8) + dup_table_slots(n) * 8);
+}
+
+extern "C" int lemon_dedup_count(lemon_ctx* ctx, const float* x, int64_t n, int d, void* workspace, int32_t* counters,
+                                 void* stream) {
+  using namespace lemon;
+  if (!ctx) return LEMON_ERR_INVALID;
+  if (!x || !workspace || !counters || n < 1 || d <= 0 || (uintptr_t(workspace) & 255))
+    return lemon_set_error(ctx, LEMON_ERR_INVALID, "dedup_count: bad args (workspace must be 256 B aligned)");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint64_t* keys = static_cast<uint64_t*>(workspace);
+  unsigned long long* table = reinterpret_cast<unsigned long long*>(static_cast<unsigned char*>(workspace) + align256(size_t(n) * 8));
+  const uint64_t slots = dup_table_slots(n);
+  LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(counters, 0, sizeof(int32_t), st));
+  LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(table, 0, slots * 8, st));
+  int64_t wblocks = (n + 7) / 8;
+  if (wblocks > int64_t(ctx->num_sms) * 16) wblocks = int64_t(ctx->num_sms) * 16;
+  hash_rows_kernel<<<unsigned(wblocks), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(x), n, d, keys, nullptr);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > int64_t(ctx->num_sms) * 8) blocks = int64_t(ctx->num_sms) * 8;
+  count_dups_kernel<<<unsigned(blocks), 256, 0, st>>>(keys, n, table, slots - 1, counters);
+  ctx->launches += 2;
+  LEMON_CUDA_CHECK(ctx, cudaGetLastError());
+  return LEMON_OK;
+}
 
 extern "C" int64_t lemon_dedup_workspace_bytes(int64_t n) {
   using namespace lemon;

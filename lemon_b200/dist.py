@@ -136,7 +136,7 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     scorer.finish_db(xdb)
     if ydb is not None:
         scorer.finish_db(ydb)
-    lab_db = txt_all[:, d].contiguous().view(torch.int32) if with_labels else None
+    lab_db = txt_all[:, d].contiguous().view(torch.int32) if (with_labels and ydb is not None) else None
     finish_text = None
     if ydb is None:
         def finish_text():

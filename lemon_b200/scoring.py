@@ -258,42 +258,53 @@ class LemonScorer:
                                                          int(bool(normalize)), _stream()), "lemon_normalize_cast")
         return Prepared(out32, out16, row_stats, stats_max, n, d, d16)
 
+    def _aligned_ws(self, nbytes: int) -> torch.Tensor:
+        ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+        return ws[(-ws.data_ptr()) % 256:]
+
     def dedup_start(self, p: Prepared) -> "dict | None":
-        """Queues the device-side grouping of bit-identical rows (lemon_dedup_build: hash -> radix sort -> run scan ->
-        bit-wise verification -> renumbering) and an asynchronous read-back of its two counters.  No host
-        synchronisation happens here; ``dedup_finish`` waits for the counters."""
-        n, dev = p.n, self.device
+        """Queues the duplicate COUNT of a database (lemon_dedup_count: row hashes into an open-addressing table, two
+        kernels) and an asynchronous read-back of the counter.  No host synchronisation happens here;
+        ``dedup_finish`` waits for the counter and only then, for databases that are worth it, runs the grouping."""
+        n = p.n
         if n < 64:
             return None
-        ws_bytes = int(self.lib.lemon_dedup_workspace_bytes(n))
-        ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
-        ws = ws[(-ws.data_ptr()) % 256:]
-        pend = {"ws": ws, "rep": torch.empty(n, dtype=torch.int32, device=dev),
-                "members": torch.empty(n, dtype=torch.int32, device=dev),
-                "offsets": torch.empty(n + 1, dtype=torch.int64, device=dev),
-                "counters": torch.empty(2, dtype=torch.int32, device=dev),
-                "host": torch.empty(2, dtype=torch.int32).pin_memory(), "event": torch.cuda.Event()}
-        with torch.cuda.device(dev):
-            self.ctx.check(self.lib.lemon_dedup_build(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(pend["ws"]), _ptr(pend["rep"]),
-                                                      _ptr(pend["members"]), _ptr(pend["offsets"]), _ptr(pend["counters"]),
-                                                      _stream()), "lemon_dedup_build")
-        pend["host"].copy_(pend["counters"], non_blocking=True)
+        pend = {"ws": self._aligned_ws(self.lib.lemon_dedup_count_workspace_bytes(n)),
+                "counters": torch.empty(2, dtype=torch.int32, device=self.device),
+                "host": self._pinned_slot(), "event": torch.cuda.Event()}
+        with torch.cuda.device(self.device):
+            self.ctx.check(self.lib.lemon_dedup_count(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(pend["ws"]),
+                                                      _ptr(pend["counters"]), _stream()), "lemon_dedup_count")
+        pend["host"].copy_(pend["counters"][:1], non_blocking=True)
         pend["event"].record()
         return pend
 
     def dedup_finish(self, p: Prepared, pend: "dict | None", min_saving: float = 0.1) -> "Dedup | None":
-        """Reads the counters of ``dedup_start`` (the path's one host round trip: the number of unique rows sizes the
-        search operands).  Returns None when fewer than `min_saving` of the rows are duplicates, or on a hash
-        collision (then nothing is de-duplicated)."""
+        """Reads the duplicate count (one host round trip per database; the number of unique rows sizes the search
+        operands).  Fewer than `min_saving` duplicate rows: None.  Otherwise the rows are grouped on the device
+        (lemon_dedup_build: radix sort of (hash, row) -> run scan -> bit-wise verification -> renumbering) and its
+        counters are read back; a hash collision (two different rows, one 63-bit hash) also returns None."""
         if pend is None:
             return None
         pend["event"].synchronize()
-        n_u, collision = int(pend["host"][0]), int(pend["host"][1])
-        pend.pop("ws")
-        if collision != 0 or n_u > (1.0 - min_saving) * p.n:
+        n, dev = p.n, self.device
+        n_dup = int(pend["host"][0])
+        pend.clear()
+        if n_dup < max(1, min_saving * n):
             return None
-        dev = self.device
-        rep = pend["rep"][:n_u]
+        rep = torch.empty(n, dtype=torch.int32, device=dev)
+        members = torch.empty(n, dtype=torch.int32, device=dev)
+        offsets = torch.empty(n + 1, dtype=torch.int64, device=dev)
+        counters = torch.empty(2, dtype=torch.int32, device=dev)
+        ws = self._aligned_ws(self.lib.lemon_dedup_workspace_bytes(n))
+        with torch.cuda.device(dev):
+            self.ctx.check(self.lib.lemon_dedup_build(self.ctx.handle, _ptr(p.f32), n, p.d, _ptr(ws), _ptr(rep), _ptr(members),
+                                                      _ptr(offsets), _ptr(counters), _stream()), "lemon_dedup_build")
+        host = counters.cpu()                                  # second round trip, only for databases with duplicates
+        n_u, collision = int(host[0]), int(host[1])
+        if collision != 0 or n_u > (1.0 - min_saving) * n:
+            return None
+        rep = rep[:n_u]
 
         def gather(src, cols, dtype):
             dst = torch.empty((n_u, cols), dtype=dtype, device=dev)
@@ -303,7 +314,7 @@ class LemonScorer:
             return dst
         uniq = Prepared(gather(p.f32, p.d, torch.float32), None if p.f16 is None else gather(p.f16, p.d16, torch.float16),
                         gather(p.row_stats, 4, torch.float32), p.stats_max, n_u, p.d, p.d16)
-        return Dedup(uniq, pend["offsets"][: n_u + 1], pend["members"], n_u)
+        return Dedup(uniq, offsets[: n_u + 1], members, n_u)
 
     def find_duplicates(self, p: Prepared, min_saving: float = 0.1) -> "Dedup | None":
         return self.dedup_finish(p, self.dedup_start(p), min_saving)

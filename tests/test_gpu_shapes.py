@@ -257,7 +257,7 @@ def test_second_pass_rescues_rows_the_fp16_pass_cannot_certify(lb):
     from lemon_b200.scoring import count_uncertified
     dev = torch.device("cuda", 0)
     n, d, kp = 100_000, 512, 31
-    x = _narrow_cone(n, d, 0.85, 11, dev)
+    x = _narrow_cone(n, d, 0.98, 11, dev)
     sc = lb.get_scorer(0)
     dbp = sc.prepare(x, True)
     qp = lemon_slice(dbp, 0, 8192)

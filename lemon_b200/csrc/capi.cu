@@ -36,15 +36,17 @@ extern "C" int lemon_ctx_create(int device, lemon_ctx** out) {
   c->launches = 0;
   c->err[0] = 0;
   c->tc_scratch = nullptr;
-  c->tc_scratch_bytes = 0;
+  c->tc_scratch_bytes = 16 * 256 * sizeof(int32_t);
+  c->tc_launch_seq = 0;
+  if (cudaMalloc(&c->tc_scratch, c->tc_scratch_bytes) != cudaSuccess) { delete c; return LEMON_ERR_CUDA; }
   c->encode_tiled = nullptr;
-  c->tune_kres = c->tune_debug = c->tune_cert = c->tune_boot = c->tune_bn = -1;
+  c->tune_kres = c->tune_debug = c->tune_cert = c->tune_boot = c->tune_bn = c->tune_pace = -1;
 #ifdef LEMON_TC_EXPERIMENT
   {
     auto env_int = [](const char* name) { const char* e = getenv(name); return e ? atoi(e) : -1; };
     c->tune_kres = env_int("LEMON_TC_KRES");       c->tune_debug = env_int("LEMON_TC_DEBUG");
     c->tune_cert = env_int("LEMON_TC_CERT");       c->tune_boot = env_int("LEMON_TC_BOOT");
-    c->tune_bn = env_int("LEMON_TC_BN");
+    c->tune_bn = env_int("LEMON_TC_BN");           c->tune_pace = env_int("LEMON_TC_PACE");
   }
 #endif
   *out = c;

@@ -53,8 +53,10 @@ normalize_cast_kernel(const float* __restrict__ in, float* __restrict__ out_f32,
 // Split-precision operands for the second tensor-core pass (rows the first pass could not certify).
 //   x = x_hi + x_lo + x_e,  x_hi = fp16(x),  x_lo = fp16(x - x_hi)   (x_lo may be an fp16 subnormal: its absolute
 //   rounding error is <= 2^-25 per component, so ||x_e|| ~ 2^-22 ||x|| instead of the 2^-11 ||x|| of one fp16 word)
-// Queries are laid out [hi | hi | lo], database rows [hi | lo | hi] (each block d16 wide), so that ONE K-loop of the
-// unchanged K1 kernel over 3*d16 columns accumulates  q_hi.b_hi + q_hi.b_lo + q_lo.b_hi  in fp32.
+// Queries are laid out [hi | lo | hi], database rows [lo | hi | hi] (each block d16 wide), so that ONE K-loop of the
+// unchanged K1 kernel over 3*d16 columns accumulates  q_hi.b_lo + q_lo.b_hi + q_hi.b_hi  in fp32 -- the two small
+// cross terms FIRST, while the partial sums are ~2^-10 of the result, so that only the last d16 additions round at
+// full magnitude and the accumulation bound stays that of a single d16-long product.
 // row_stats / stats_max are written in the layout lemon_rerank reads, with the residual ||x_e|| in the place of the
 // one-word rounding error:  {||x||, ||x||, ||x_e||, ||x||^2}  and maxima  {||x||, ||x||, ||x_e||, | ||x||^2 - 1 |}.
 __global__ void __launch_bounds__(256)
@@ -74,9 +76,9 @@ split_cast_kernel(const float* __restrict__ x, __half* __restrict__ out, float* 
       const __half lo = __float2half_rn(r1);
       const float e = r1 - __half2float(lo);            // exact in fp32
       sx = fmaf(v, v, sx); se = fmaf(e, e, se);
-      o[c] = hi;
-      o[d16 + c] = role == 0 ? hi : lo;
-      o[2 * d16 + c] = role == 0 ? lo : hi;
+      o[c] = role == 0 ? hi : lo;
+      o[d16 + c] = role == 0 ? lo : hi;
+      o[2 * d16 + c] = hi;
     }
     sx = warp_sum(sx); se = warp_sum(se);
     const float nx = sqrtf(sx), ne = sqrtf(se);

@@ -49,6 +49,8 @@ struct TcParams {
   int cert;             // ladder: exceedance count that certifies a level (`keep` of the C ABI)
   int boot_tiles;       // 256-column tiles per item that only bootstrap the thresholds (8 or 16; 0 = off)
   int debug;            // experiments (-DLEMON_TC_EXPERIMENT builds): 1 = epilogue does no work, 2 = filter only
+  int32_t* progress;    // [n_units] tile steps issued by every CTA pair (zeroed before the launch); nullptr = no pacing
+  int pace_window;      // a pair may run at most this many tile steps ahead of the slowest pair
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -427,6 +429,27 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------------------------- DB-walk pacing
+// All CTA pairs stream the same DB segment in the same order, and the DB (0.4 - 5 GB of fp16) does not fit in L2.
+// Left alone the pairs drift apart by more tiles than L2 can hold, and then EVERY pair fetches EVERY tile from DRAM
+// itself (ncu, 412 500 x 3.3 M x 768 launch: 6.75 TB of DRAM reads instead of ~0.11 TB, 37 % of the DRAM bandwidth --
+// power that the 1000 W cap takes away from the tensor cores).  Pacing keeps the pairs within `pace_window` tile steps
+// of the slowest one: every pair publishes the number of tile steps it has issued; the otherwise idle warp 3 of the
+// leader CTA polls the minimum over all pairs and posts "issue up to here" in shared memory; the TMA producer
+// checks that word before each tile.  It is a performance hint only: the producer's wait is bounded and on timeout
+// the pair stops pacing for the rest of the launch (and reports "infinitely far", so nobody waits for it).
+constexpr int kPaceWindow = 24;                // tile steps (d = 768: 24 x 393 KB = 9.4 MB of DB inside the window)
+constexpr int kPaceMaxSpins = 4000;            // x ~100 ns: a pair waits at most ~0.4 ms per check before it gives up
+constexpr int kPaceFar = 0x3fffffff;
+__device__ __forceinline__ int ld_volatile_global(const int32_t* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_global(int32_t* p, int v) {
+  asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ kernel
 template <int CG, int BN>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -459,12 +482,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   // per-row threshold exchange between the two epilogue groups: [2][128] x (item tag << 32 | float bits)
   volatile uint64_t* th_sh = reinterpret_cast<volatile uint64_t*>(smem_raw + (a_full + 96 - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  volatile int* pace_go = reinterpret_cast<volatile int*>(smem_raw + (a_full + 88 - smem_u32(smem_raw)));     // issue limit
+  volatile int* pace_done = pace_go + 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
     for (int b = 0; b < int(kNBuf); ++b) { mbar_init(tmem_full + 8 * b, 1); mbar_init(tmem_empty + 8 * b, CG * 4 * kEpiGroups); }
+    *pace_go = p.pace_window;
+    *pace_done = 0;
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<CG>(tmem_slot, kTmemCols);
@@ -479,6 +506,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
       const uint32_t full0 = (CG == 2) ? mapa_rank0(full_bar(0)) : full_bar(0);   // leader's barriers
       const uint32_t afull_l = (CG == 2) ? mapa_rank0(a_full) : a_full;
       int stage = 0; uint32_t phase = 0; uint32_t it = 0;
+      int gstep = 0;                                              // tile steps issued so far in this launch
+      bool pace = p.progress != nullptr && cta_rank == 0;
       for (int64_t item = unit; item < p.n_items; item += n_units, ++it) {
         const int64_t rt = item / p.nseg, seg = item % p.nseg;
         const int64_t col0 = seg * p.seg_len;
@@ -492,7 +521,13 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
         for (int kc = 0; kc < p.kres; ++kc)
           tma_load_2d<CG>(a_smem + kc * kAChunkBytes, &map_q, afull_l, kc * kBK, row0);
         const int64_t nsteps = ntiles + (ntiles >= kBootMinTiles ? kBoot : 0);   // bootstrap tiles are scanned twice
-        for (int64_t i = 0; i < nsteps; ++i) {
+        for (int64_t i = 0; i < nsteps; ++i, ++gstep) {
+          if (pace) {                                             // stay within the window of the slowest pair
+            st_volatile_global(p.progress + unit, gstep);
+            int spins = 0;
+            while (gstep >= *pace_go && spins < kPaceMaxSpins) { __nanosleep(100); ++spins; }
+            if (spins >= kPaceMaxSpins) { pace = false; st_volatile_global(p.progress + unit, kPaceFar); }
+          }
           const int64_t t = i < ntiles ? i : i - ntiles;
           const int dbrow = int(col0 + t * BN + cta_rank * kBRows);
           for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -508,6 +543,18 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
             if (++stage == p.nstage) { stage = 0; phase ^= 1; }
           }
         }
+      }
+      if (p.progress != nullptr && cta_rank == 0) { st_volatile_global(p.progress + unit, kPaceFar); *pace_done = 1; }
+    }
+  } else if (warp == 3) {
+    // =============================== pacer (leader CTA): slowest pair's progress -> issue limit ===============================
+    if (p.progress != nullptr && cta_rank == 0) {
+      while (__shfl_sync(kFull, *pace_done, 0) == 0) {          // lane 0's view: the exit must be warp-uniform
+        int mn = kPaceFar;
+        for (int u = lane; u < int(n_units); u += 32) mn = min(mn, ld_volatile_global(p.progress + u));
+        mn = __reduce_min_sync(kFull, mn);
+        if (lane == 0) *pace_go = mn >= kPaceFar ? 0x7fffffff : mn + p.pace_window;
+        __nanosleep(400);
       }
     }
   } else if (warp == 1) {
@@ -781,6 +828,9 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   const int64_t row_tiles = (nq + kBM * CG - 1) / (kBM * CG);
   p.n_items = row_tiles * nseg;
   p.cand_keys = cand_keys; p.cand_cnt = cand_cnt; p.cand_theta = cand_theta;
+  // pacing (see "DB-walk pacing" above): only when the DB is scanned by several pairs and is long enough to drift
+  p.progress = nullptr;
+  p.pace_window = ctx->tune_pace >= 0 ? ctx->tune_pace : kPaceWindow;
   // tuning knobs: library defaults unless the ctx was created by a -DLEMON_TC_EXPERIMENT build (capi.cu)
   p.debug = ctx->tune_debug > 0 ? ctx->tune_debug : 0;
   p.cert = (ctx->tune_cert >= 16 && ctx->tune_cert <= kKeep) ? ctx->tune_cert : keep;
@@ -795,6 +845,11 @@ static int launch_tc(lemon_ctx* ctx, const void* q16, const void* db16, int64_t 
   rc = make_map(ctx, &map_db, db16, m, d16, BN / CG);
   if (rc) return rc;
 
+  if (p.pace_window > 0 && ctx->tc_scratch && units > 1 && nseg == 1 && seg_len / BN >= 4 * p.pace_window) {
+    constexpr int kSlots = 16, kSlotInts = 256;          // a ring of progress arrays: launches in flight never share one
+    p.progress = static_cast<int32_t*>(ctx->tc_scratch) + (ctx->tc_launch_seq++ % kSlots) * kSlotInts;
+    LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(p.progress, 0, kSlotInts * sizeof(int32_t), stream));
+  }
   auto kern = knn_tc_kernel<CG, BN>;
   LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   cudaLaunchConfig_t cfg = {};

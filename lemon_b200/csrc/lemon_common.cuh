@@ -13,13 +13,14 @@ struct lemon_ctx {
   int cc_major, cc_minor;
   int64_t launches;
   char err[512];
-  // tensor-core kernel scratch (per-CTA streaming top-k buffers), grown on demand
+  // tensor-core kernel scratch: a ring of 16 progress arrays (256 int32 each) for K1's DB-walk pacing
   void* tc_scratch;
   size_t tc_scratch_bytes;
+  unsigned tc_launch_seq;
   void* encode_tiled;   // cuTensorMapEncodeTiled, resolved lazily
   // K1 tuning knobs; -1 = library default.  Only builds with -DLEMON_TC_EXPERIMENT read them from the environment
   // (once, at ctx creation); the product build always runs the defaults.
-  int tune_kres, tune_debug, tune_cert, tune_boot, tune_bn;
+  int tune_kres, tune_debug, tune_cert, tune_boot, tune_bn, tune_pace;
 };
 
 int lemon_set_error(lemon_ctx* ctx, int code, const char* fmt, ...);

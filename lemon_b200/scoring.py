@@ -118,6 +118,14 @@ def query_in_db_from_indices(n_queries: int, train_indices_in_compr) -> np.ndarr
     return out
 
 
+def acc_eps_coef_split(d16: int, d: int) -> float:
+    """Accumulation bound of the split-precision second pass (operands [hi | lo | hi] x [lo | hi | hi], d16 columns
+    per block).  The two cross terms are accumulated first, while the partial sums are <= 2^-10 ||q|| ||b||, so only
+    the last d16 additions round at full magnitude: d16 * 2^-23 * (1 + 2^-8) covers all 3 * d16 of them.  Plus the
+    fp32 re-evaluation term of acc_eps_coef and the neglected q_lo.b_lo product (<= 2^-22 ||q|| ||b||, counted 2^-21)."""
+    return float(d16) * 2.0 ** -23 * (1.0 + 2.0 ** -8) + (d / 32.0 + 6.0) * 2.0 ** -24 + 2.0 ** -21
+
+
 def count_uncertified(info: dict) -> "int | None":
     """Rows of a kNN call (``LemonScorer.last_info`` of one side) that the re-rank certificate sent to the exact
     fp32 kernel.  Reads the device counters: synchronises."""
@@ -409,7 +417,7 @@ class LemonScorer:
 
     # ------------------------------------------------ second tensor-core pass (split precision)
     def split_operands(self, p: Prepared, role: int) -> Prepared:
-        """[hi | hi | lo] (role 0, queries) / [hi | lo | hi] (role 1, database) fp16 operands of 3*d16 columns and the
+        """[hi | lo | hi] (role 0, queries) / [lo | hi | hi] (role 1, database) fp16 operands of 3*d16 columns and the
         statistics of the residual (include/lemon_b200.h: lemon_split_cast)."""
         d16 = p.d16
         out16 = torch.empty((p.n, 3 * d16), dtype=torch.float16, device=self.device)
@@ -442,7 +450,7 @@ class LemonScorer:
             dbs = db._split = self.split_operands(db, 1)         # built on first use, kept with the staged database
         *cand, _ = self.knn_candidates(q2s, dbs, keep=MAX_KP)
         _, _, uncert, n_unc = self.rerank(q2s, dbs, cand, kp, metric, out=out, out_rows=rows,
-                                          acc_coef=acc_eps_coef(dbs.d16, db.d) + 2.0 ** -21)     # + the q_lo.b_lo term
+                                          acc_coef=acc_eps_coef_split(db.d16, db.d))
         return uncert, n_unc
 
     def knn(self, q: Prepared, db: Prepared, kp: int, metric: int, mode: str | None = None):

@@ -28,7 +28,9 @@ def cone(shared):
 
 
 res = []
-for name, shared in (("iid-gaussian", 0.0), ("cone 0.7", 0.7), ("cone 0.9", 0.9), ("cone 0.98", 0.98), ("degenerate (cone 0.9999)", 0.9999)):
+shares = [float(a) for a in sys.argv[4:]] or [0.0, 0.7, 0.9, 0.98, 0.9999]
+for shared in shares:
+    name = "iid-gaussian" if shared == 0 else ("degenerate (cone %g)" % shared if shared > 0.999 else "cone %g" % shared)
     x = cone(shared)
     dbp = sc.prepare(x, True)
     del x

@@ -7,20 +7,22 @@
 namespace lemon {
 
 constexpr int kRrWarps = 8;
-constexpr int kSelCap = 1024;            // selection buffer (keys) per warp; a chunk adds at most kRrChunk = 512
+constexpr int kSelCap = 512;             // selection buffer (keys) per warp; a chunk adds at most kRrChunk = 256
+                                         // (6 KB of shared memory per warp with the exact-key buffer: 32 warps per SM)
 
-// loads one chunk = 512 slots of a candidate list (16 keys per lane); invalid slots become 0
-constexpr int kRrChunk = 512;
+// loads one chunk = 256 slots of a candidate list (8 keys per lane); invalid slots become 0
+constexpr int kRrChunk = 256;
+constexpr int kRrPerLane = kRrChunk / 32;
 constexpr int kRrChunksPerList = kListCap / kRrChunk;
-static_assert(kListCap % kRrChunk == 0, "candidate lists are read in 512-key chunks");
+static_assert(kListCap % kRrChunk == 0, "candidate lists are read in 256-key chunks");
 __device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_keys, const int32_t* __restrict__ cand_cnt,
-                                           int64_t row, int nlist, int chunk, int lane, uint64_t (&k)[16], int& tot) {
+                                           int64_t row, int nlist, int chunk, int lane, uint64_t (&k)[kRrPerLane], int& tot) {
   const int l = chunk / kRrChunksPerList, part = chunk % kRrChunksPerList;
   const int c = max(0, min(min(cand_cnt[row * nlist + l], kListCap) - part * kRrChunk, kRrChunk));
   tot = c;
   const uint64_t* src = cand_keys + (row * nlist + l) * kListCap + part * kRrChunk;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < kRrPerLane; ++i) {
     const int e = i * 32 + lane;                      // coalesced: consecutive lanes read consecutive keys
     k[i] = e < c ? __ldg(src + e) : 0ull;
   }
@@ -98,13 +100,13 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
       }
       return lo;
     };
-    uint64_t k[16];
+    uint64_t k[kRrPerLane];
     int tot;
     for (int c = 0; c < nchunk; ++c) {
       load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
       if (tot == 0) continue;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kRrPerLane; ++i) {
         const bool pred = k[i] != 0ull && uint32_t(k[i] >> 32) >= keep_bits && uint32_t(key_idx(k[i])) < uint32_t(m);
         const unsigned mask = __ballot_sync(kFull, pred);
         const int pos = n + __popc(mask & ((1u << lane) - 1u));
@@ -199,9 +201,9 @@ extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, con
   LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(n_uncert, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kRrWarps - 1) / kRrWarps;
-  const int64_t cap = int64_t(ctx->num_sms) * 8;
+  const int64_t cap = int64_t(ctx->num_sms) * 8;      // two waves of four resident blocks
   if (blocks > cap) blocks = cap;
-  const size_t smem = size_t(kRrWarps) * (kSelCap + kCap) * sizeof(uint64_t);     // 80 KB: two blocks per SM
+  const size_t smem = size_t(kRrWarps) * (kSelCap + kCap) * sizeof(uint64_t);     // 48 KB: four blocks per SM
   LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(rerank_kernel<LEMON_METRIC_IP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   LEMON_CUDA_CHECK(ctx, cudaFuncSetAttribute(rerank_kernel<LEMON_METRIC_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   if (metric == LEMON_METRIC_IP)

@@ -54,19 +54,20 @@ class OracleScorer:
         from oracle import lemon_oracle as O
         return torch.from_numpy(O.dists_tr(a.numpy(), b.numpy(), "cosine" if metric == 0 else "euclidean"))
 
-    def emit(self, xq, yq, xdb, ydb, dists_tr, topn, topm, *, k, kp, metric, qid, hparams, **_):
+    def emit(self, xq, yq, xdb, ydb, dists_tr, topn, topm, *, k, kp, metric, qid, hparams, lab_q=None, lab_db=None, **_):
         from oracle import lemon_oracle as O
         dist_type = "cosine" if metric == 0 else "euclidean"
         in_db = qid.numpy() >= 0
         Dn, In = O.apply_self_exclusion(topn[0].numpy(), topn[1].numpy().astype(np.int64), in_db)
         Dm, Im = O.apply_self_exclusion(topm[0].numpy(), topm[1].numpy().astype(np.int64), in_db)
-        rec = O.build_records(xq.f32.numpy(), yq.f32.numpy(), xdb.f32.numpy(), ydb.f32.numpy(), Dn, In, Dm, Im, dist_type)
+        rec = O.build_records(xq.f32.numpy(), yq.f32.numpy(), xdb.f32.numpy(), ydb.f32.numpy(), Dn, In, Dm, Im, dist_type,
+                              None if lab_q is None else lab_q.numpy(), None if lab_db is None else lab_db.numpy())
         score, sn, sm = O.calc_scores_vectorized(rec, hparams)
         return {"score": torch.from_numpy(score), "I_n": torch.from_numpy(In), "I_m": torch.from_numpy(Im),
                 "d_1": torch.from_numpy(rec["d_1"])}
 
 
-def _worker(rank, world, port, n, d, k, q):
+def _worker(rank, world, port, n, d, k, q, with_labels=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -78,13 +79,18 @@ def _worker(rank, world, port, n, d, k, q):
         hp = {"beta": 5.0, "gamma": 5.0, "tau_1_n": 0.1, "tau_2_n": 5.0, "tau_1_m": 0.1, "tau_2_m": 5.0}
         g = ldist.allgather_rows(pad(x), n)
         assert g.shape == (n, d) and np.array_equal(g.numpy(), x)       # padding never enters the DB
-        out = ldist.score_pairs_sharded(pad(x), pad(y), n, k=k, hparams=hp, scorer=OracleScorer())
+        lab_local = None
+        if with_labels:      # label ids travel as extra columns of the text all-gather (no third collective)
+            lab = (np.arange(n) * 7 % 5).astype(np.int32)
+            lab_local = torch.from_numpy(np.concatenate([lab[r0:r1], np.full(per - (r1 - r0), -9, np.int32)]))
+        out = ldist.score_pairs_sharded(pad(x), pad(y), n, k=k, hparams=hp, scorer=OracleScorer(), text_label_ids_local=lab_local)
         q.put((rank, out["rows"], out["score"].numpy(), out["I_n"].numpy()))
     finally:
         dist.destroy_process_group()
 
 
-def test_sharded_equals_single_rank_gloo():
+@pytest.mark.parametrize("with_labels", [False, True])
+def test_sharded_equals_single_rank_gloo(with_labels):
     from oracle import lemon_oracle as O
     n, d, k, world = 101, 16, 4, 2           # odd n: the last shard is padded
     with socket.socket() as s:
@@ -92,7 +98,7 @@ def test_sharded_equals_single_rank_gloo():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, k, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, d, k, q, with_labels)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=120) for _ in range(world))
@@ -103,7 +109,8 @@ def test_sharded_equals_single_rank_gloo():
     x = rng.standard_normal((n, d)).astype(np.float32)
     y = rng.standard_normal((n, d)).astype(np.float32)
     hp = {"beta": 5.0, "gamma": 5.0, "tau_1_n": 0.1, "tau_2_n": 5.0, "tau_1_m": 0.1, "tau_2_m": 5.0}
-    full = O.lemon_oracle(x, y, x, y, k=k, query_in_db=np.arange(n), hparams=hp)
+    lab = (np.arange(n) * 7 % 5).astype(np.int32) if with_labels else None
+    full = O.lemon_oracle(x, y, x, y, k=k, query_in_db=np.arange(n), hparams=hp, text_label_ids_q=lab, text_label_ids_db=lab)
     score = np.concatenate([r[2] for r in res])
     I_n = np.concatenate([r[3] for r in res])
     assert res[0][1] == (0, 51) and res[1][1] == (51, 101)

@@ -150,15 +150,16 @@ def load_peaks():
     return {"burst": 1590.0, "sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
 
 
-def k1_traffic(workload):
-    """DRAM bytes per K1 launch of THIS workload's launch shape from the committed ncu captures
-    (profiles/k1_traffic.json: {workload: {dram_bytes_per_launch, note}}), or None."""
+def k1_traffic(workload, world):
+    """DRAM bytes per K1 launch of THIS run's dominant launch shape from the committed ncu captures
+    (profiles/k1_traffic.json: {"<workload>@<n_gpus>": {dram_bytes_per_launch, note}}), or None when no capture of
+    that shape exists."""
     p = os.path.join(ROOT, "profiles", "k1_traffic.json")
     try:
         j = json.load(open(p))
     except Exception:
         return None
-    return j.get(workload)
+    return j.get(f"{workload}@{world}")
 
 
 def bench_config(wl, world):
@@ -479,7 +480,7 @@ def main():
 
     peaks = load_peaks()
     ach = big / (k1_ms * 1e-3) / 1e12
-    traffic = k1_traffic(args.workload)
+    traffic = k1_traffic(args.workload, world)
     roofline = {"bound": "tensor", "kernel": "knn_tc_kernel (K1: fused tcgen05 similarity + streaming top-k)",
                 "achieved": ach, "peak": peaks["sustained"], "unit": "TFLOP/s", "frac": ach / peaks["sustained"],
                 "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "frac_of_burst_peak": ach / peaks["burst"],

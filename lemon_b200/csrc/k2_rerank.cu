@@ -29,7 +29,7 @@ __device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_key
 }
 
 template <int METRIC>
-__global__ void __launch_bounds__(kRrWarps * 32)
+__global__ void __launch_bounds__(kRrWarps * 32, 4)
 rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const uint64_t* __restrict__ cand_keys,
               const int32_t* __restrict__ cand_cnt, const float* __restrict__ cand_theta,
               const float* __restrict__ q_row_stats, const float* __restrict__ db_stats_max, float acc_eps, int64_t nq,

@@ -400,7 +400,8 @@ def main():
     nseg = {s: info[s].get("nseg") for s in ("img", "txt")}
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = parity_gate(out, (r0, r1), x_host, y_host, wl, args.parity_rows, lab_host)
+        n_rows = args.parity_rows if n <= 1_000_000 else min(args.parity_rows, 256)      # the oracle is O(rows x N x d) on the host
+        parity = parity_gate(out, (r0, r1), x_host, y_host, wl, n_rows, lab_host)
         parity["uncertified_rows_per_step"] = n_unc
     barrier()
 

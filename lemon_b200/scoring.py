@@ -147,16 +147,23 @@ def _slice_prepared(p: "Prepared", r0: int, r1: int) -> "Prepared":
 
 
 def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512) -> int:
-    """Number of DB segments the tensor-core kernel scans independently.  Work items are
-    (row tile, segment); more segments even out the last wave when there are few row
-    tiles, at the price of nseg*64 candidates per row for the re-rank and of a fixed
-    start-up + merge cost per item (measured on B200: ~0.85 ms at d=512, i.e. the MMA
-    time of ~60k columns)."""
+    """Number of DB segments the tensor-core kernel scans independently.  Work items are (row tile, segment); more
+    segments fill the CTA pairs when there are fewer row tiles than pairs, at the price of 2 more candidate lists per
+    row and segment for the re-rank and of a fixed cost per wave of items.  Calibrated on B200 with the round-2 kernel
+    (profiles/r02_plan_calibrate.log): a wave costs its columns plus ~0.08 ms (d = 512) / ~0.14 ms (d = 768), i.e. the
+    MMA time of ~6000 columns either way; one row tile against 370 000 columns: 5.1 ms unsplit, 0.42 ms in 16
+    segments, 0.16 ms in 64.  Launches of two or more full rounds are never split (their lists would double for a gain
+    the tail launch of plan_tail gets more cheaply, and only unsplit launches pace their DB walk)."""
     units = max(1, num_sms // cta_group)
     tiles = max(1, -(-nq // (128 * cta_group)))
-    overhead_cols = 3.0e7 / max(d16, 64)
+    if tiles >= 2 * units:
+        return 1
+    overhead_cols = 6000.0
+    cands = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64}
+    if tiles < units:
+        cands.add(min(64, units // tiles))          # exactly one wave
     best, best_cost = 1, None
-    for nseg in (1, 2, 3, 4, 6, 8, 12, 16):
+    for nseg in sorted(cands):
         if nseg > 1 and m // nseg < 4096:
             break
         items = tiles * nseg
@@ -179,7 +186,7 @@ def plan_tail(nq: int, m: int, num_sms: int, cta_group: int) -> tuple[int, int]:
     tail = tiles - full
     if full == 0 or tail == 0 or tail > 0.6 * units:
         return nq, 1
-    nseg = min(units // tail, 8)
+    nseg = min(units // tail, 16)
     while nseg > 1 and m // nseg < 4096:
         nseg -= 1
     if nseg <= 1:

@@ -144,3 +144,23 @@ def test_embedding_handoff_equals_score_pairs_on_the_same_embeddings():
     for c, t in ref.items():
         if c != "rows":
             assert torch.equal(got[c], t), c
+
+
+def test_sharded_driver_host_inputs_with_labels_and_host_outputs():
+    """The C1-shaped bench path end to end: pinned HOST shards, label ids, mass-duplicate text side (10 distinct
+    prompts -> de-duplicated search), streamed host outputs; equals the device-resident call bit for bit."""
+    import torch
+    import lemon_b200
+    from lemon_b200 import dist as ldist
+    x, y, lab, _ = clustered_pairs(12_000, 512, n_clusters=60, seed=10, dup_text_classes=10)
+    dev = torch.device("cuda", 0)
+    sc = lemon_b200.get_scorer(0)
+    lab_t = torch.from_numpy(lab.astype(np.int32))
+    ref = ldist.score_pairs_sharded(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), 12_000, k=30, hparams=HP, scorer=sc,
+                                    text_label_ids_local=lab_t.to(dev))
+    assert sc.last_info["txt"].get("n_unique") == 10
+    got = ldist.score_pairs_sharded(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), 12_000, k=30, hparams=HP,
+                                    scorer=sc, text_label_ids_local=lab_t, host_out={})
+    for c, t in ref.items():
+        if c != "rows":
+            assert torch.equal(got[c], t.cpu()), c

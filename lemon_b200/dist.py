@@ -65,20 +65,21 @@ def _side_stream(dev, which: str):
 def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type: str = "cosine",
                         hparams=None, normalize: bool = True, return_records: bool = True, scorer=None,
                         group=None, text_label_ids_local=None, host_out: dict | None = None,
-                        index_dtype=torch.int64, d2h_parts: int = 4) -> dict:
+                        index_dtype=torch.int64, d2h_parts: int = 4, h2d_chunks: int = 4) -> dict:
     """Every rank passes its padded shard [per, d] of both modalities.  The DB is all pairs (train-split
     self-exclusion on, query_in_db = own global row ids).  Returns this rank's rows of every output (see
     lemon_b200.score_pairs) plus 'rows' = (r0, r1).
 
     Shards may be device tensors or (pinned) HOST tensors.  With host tensors both host->device copies are
-    issued up front on a copy stream and the whole image side (all-gather, K0, K1, K2a) runs while the text
-    shard is still in flight; the text side starts when its copy has landed.
+    issued up front on a copy stream in `h2d_chunks` pieces; every piece is all-gathered and normalised on a side
+    stream as soon as it has landed (lemon_b200.handoff.ShardStager), so one piece of the image copy is exposed and
+    the text side is staged behind the image-side kernels.
 
     host_out: dict of pinned host tensors (one per output column, at least r1-r0 rows; missing ones are created
     and added).  The records are then produced in `d2h_parts` row parts and each part's device->host copy runs on
     a copy stream while the next part is being computed; the call returns host tensors once all copies have
     landed.  index_dtype=torch.int32 halves the bytes of I_n / I_m (faiss's int64 is the default)."""
-    from .scoring import METRIC, _slice_prepared, _to_dev
+    from .scoring import METRIC
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     r0, r1, per = shard_bounds(n_total, world, rank)
@@ -91,59 +92,55 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     d = img_local.shape[1]
     with_labels = text_label_ids_local is not None
     main = torch.cuda.current_stream(dev) if on_gpu else None
-    e_txt = None
-
-    def stage_text(t):
-        """The text shard as it is all-gathered: [per, d], or [per, d + LABEL_COLS] with the label ids."""
-        if not with_labels:
-            return t.to(dev, non_blocking=True)
-        wide = torch.zeros((per, d + LABEL_COLS), dtype=torch.float32, device=dev)
-        wide[:, :d].copy_(t, non_blocking=True)
-        lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
-        wide[:, d].copy_(lab.view(torch.float32))
-        return wide
-
-    if on_gpu and not img_local.is_cuda:
+    metric = METRIC[dist_type]
+    if on_gpu and not img_local.is_cuda and d % 4 == 0:
+        # ---- host shards: the copies are cut into chunks on a copy stream; every chunk is all-gathered and normalised
+        # on a side stream as soon as it has landed, so only one chunk of the image copy is exposed and the whole text
+        # side is staged behind the image-side kernels
+        from .handoff import ShardStager
         cs = _side_stream(dev, "h2d")
         cs.wait_stream(main)
+        st_img = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks)
+        st_txt = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks, LABEL_COLS if with_labels else 0)
+        step = max(1, -(-per // max(1, h2d_chunks)))
         with torch.cuda.stream(cs):
-            img_local = img_local.to(dev, non_blocking=True)
-            e_img = torch.cuda.Event()
-            e_img.record(cs)
-            txt_wide = stage_text(txt_local)
-            e_txt = torch.cuda.Event()
-            e_txt.record(cs)
-        img_local.record_stream(main)
-        txt_wide.record_stream(main)
-        main.wait_event(e_img)
-    else:
-        txt_wide = stage_text(txt_local)
-    metric = METRIC[dist_type]
-    kp = k + 1
-    # ---- image side (run_lemon.py:164,168/172,176,235) while the text shard may still be copying
-    xdb = scorer.prepare_db(allgather_rows(img_local, n_total, group), normalize, defer_dedup=True)
-    ydb = txt_all = None
+            for a in range(0, per, step):
+                st_img.append(img_local[a:a + step])
+            if with_labels:
+                lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
+                st_txt.shard[:, d].copy_(lab.view(torch.float32))
+            for a in range(0, per, step):
+                st_txt.append(txt_local[a:a + step], cols=slice(0, d))
+        xdb = st_img.finish(after=cs)
+        xdb._pending = scorer.dedup_start(xdb) if getattr(scorer, "dedup", False) else None
+        scorer.finish_db(xdb)
 
-    def stage_text_db():
-        nonlocal txt_all
-        txt_all = allgather_rows(txt_wide, n_total, group)
-        return scorer.prepare_db(txt_all[:, :d] if with_labels else txt_all, normalize, defer_dedup=True)
-
-    if e_txt is None:
-        # device-resident shards: stage the text side too before the long kernels are queued, so that the duplicate
-        # detection of both matrices costs ONE host round trip (it reads their counters back)
-        ydb = stage_text_db()
-    scorer.finish_db(xdb)
-    if ydb is not None:
-        scorer.finish_db(ydb)
-    lab_db = txt_all[:, d].contiguous().view(torch.int32) if (with_labels and ydb is not None) else None
-    finish_text = None
-    if ydb is None:
         def finish_text():
-            main.wait_event(e_txt)
-            return scorer.finish_db(stage_text_db()), (txt_all[:, d].contiguous().view(torch.int32) if with_labels else None)
+            ydb = st_txt.finish(after=cs)
+            ydb._pending = scorer.dedup_start(ydb) if getattr(scorer, "dedup", False) else None
+            return scorer.finish_db(ydb), st_txt.labels[:n_total] if with_labels else None
+        return score_staged(scorer, xdb, None, (r0, r1, per), k=k, metric=metric, hparams=hparams, return_records=return_records,
+                            lab_db=None, host_out=host_out, index_dtype=index_dtype, d2h_parts=d2h_parts, late_text=finish_text)
+
+    # ---- device-resident shards
+    if with_labels:     # the text shard as it is all-gathered: [per, d + LABEL_COLS] with the label ids
+        txt_wide = torch.zeros((per, d + LABEL_COLS), dtype=torch.float32, device=dev)
+        txt_wide[:, :d].copy_(txt_local, non_blocking=True)
+        lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
+        txt_wide[:, d].copy_(lab.view(torch.float32))
+    else:
+        txt_wide = txt_local.to(dev, non_blocking=True)
+    img_local = img_local.to(dev, non_blocking=True)
+    # image and text databases are staged before the long kernels are queued, so that the duplicate detection of both
+    # matrices costs ONE host round trip (it reads their counters back)
+    xdb = scorer.prepare_db(allgather_rows(img_local, n_total, group), normalize, defer_dedup=True)
+    txt_all = allgather_rows(txt_wide, n_total, group)
+    ydb = scorer.prepare_db(txt_all[:, :d] if with_labels else txt_all, normalize, defer_dedup=True)
+    scorer.finish_db(xdb)
+    scorer.finish_db(ydb)
+    lab_db = txt_all[:, d].contiguous().view(torch.int32) if with_labels else None
     return score_staged(scorer, xdb, ydb, (r0, r1, per), k=k, metric=metric, hparams=hparams, return_records=return_records,
-                        lab_db=lab_db, host_out=host_out, index_dtype=index_dtype, d2h_parts=d2h_parts, late_text=finish_text)
+                        lab_db=lab_db, host_out=host_out, index_dtype=index_dtype, d2h_parts=d2h_parts)
 
 
 def score_staged(scorer, xdb, ydb, bounds, *, k: int, metric: int, hparams=None, return_records: bool = True, lab_db=None,

@@ -21,31 +21,39 @@ from .scoring import METRIC, Prepared, _ptr, get_scorer
 
 
 class ShardStager:
-    """Collects one modality's features of this rank ([per, d], filled front to back) and stages the replicated
-    database operands chunk by chunk on a side stream."""
+    """Collects one modality's rows of this rank ([per, d], filled front to back, from the device or from pinned host
+    memory) and stages the replicated database operands chunk by chunk on a side stream: all-gather of the chunk (NCCL),
+    then K0 (normalise, fp16 copy, statistics) into the chunk's rows of the database.  With `label_cols` the shard rows
+    carry that many extra fp32 columns after the embedding (column 0 of them = the int32 label id of the discrete text
+    metric); they travel in the same all-gather and K0 reads the embedding columns through its row stride."""
 
-    def __init__(self, scorer, n_total: int, bounds, d: int, normalize: bool, group, chunks: int):
+    def __init__(self, scorer, n_total: int, bounds, d: int, normalize: bool, group, chunks: int, label_cols: int = 0):
         self.sc, self.n, self.group, self.normalize = scorer, n_total, group, normalize
         self.r0, self.r1, self.per = bounds
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         dev = scorer.device
-        assert d % 4 == 0, "embedding width must be a multiple of 4"
-        self.d, self.d16 = d, -(-d // 64) * 64
-        self.shard = torch.zeros((self.per, d), dtype=torch.float32, device=dev)
+        assert d % 4 == 0 and label_cols % 4 == 0, "row widths must be multiples of 4 floats (16 B)"
+        self.d, self.d16, self.d_in = d, -(-d // 64) * 64, d + label_cols
+        self.shard = torch.zeros((self.per, self.d_in), dtype=torch.float32, device=dev)
         rows = self.world * self.per                       # padded row space; the operands are sliced to n_total at the end
         self.f32 = torch.empty((rows, d), dtype=torch.float32, device=dev)
         self.f16 = torch.empty((rows, self.d16), dtype=torch.float16, device=dev)
         self.stats = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+        self.labels = torch.empty(rows, dtype=torch.int32, device=dev) if label_cols else None
         self.chunk = max(1, -(-self.per // max(1, chunks)))
         self.maxima = []                                   # one [4] tensor per K0 call
-        self.filled = 0                                    # rows written by the encoder
+        self.filled = 0                                    # rows written into the shard
         self.staged = 0                                    # rows handed to the side stream
         self.side = torch.cuda.Stream(dev)
 
-    def append(self, feats: torch.Tensor):
-        b = feats.shape[0]
-        assert self.filled + b <= self.per and feats.shape[1] == self.d
-        self.shard[self.filled:self.filled + b].copy_(feats)          # dtype conversion (bf16 autocast -> fp32) included
+    def append(self, rows: torch.Tensor, cols: "slice | None" = None):
+        """rows: [b, d_in] (or [b, width of `cols`]) device or pinned host tensor; copied on the CURRENT stream."""
+        b = rows.shape[0]
+        assert self.filled + b <= self.per
+        dst = self.shard[self.filled:self.filled + b]
+        dst = dst if cols is None else dst[:, cols]
+        assert rows.shape[1] == dst.shape[1]
+        dst.copy_(rows, non_blocking=True)                 # dtype conversion (bf16 autocast -> fp32) included
         self.filled += b
         while self.filled - self.staged >= self.chunk:
             self._stage(self.staged, self.staged + self.chunk)
@@ -57,32 +65,40 @@ class ShardStager:
         with torch.cuda.device(sc.device):
             sc.ctx.check(sc.lib.lemon_normalize_cast(
                 sc.ctx.handle, _ptr(src), _ptr(self.f32[row0:row0 + nrows]), _ptr(self.f16[row0:row0 + nrows]),
-                _ptr(self.stats[row0:row0 + nrows]), _ptr(mx), nrows, self.d, self.d16, self.d, int(bool(self.normalize)),
+                _ptr(self.stats[row0:row0 + nrows]), _ptr(mx), nrows, self.d, self.d16, self.d_in, int(bool(self.normalize)),
                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lemon_normalize_cast")
 
     def _stage(self, c0: int, c1: int):
-        """all-gather rows [c0, c1) of every rank's shard and run K0 on them, on the side stream"""
-        main = torch.cuda.current_stream(self.sc.device)
+        """all-gather rows [c0, c1) of every rank's shard and run K0 on them, on the side stream (which first waits for
+        what the current stream has queued so far, i.e. for the copies of those rows)"""
+        cur = torch.cuda.current_stream(self.sc.device)
         ev = torch.cuda.Event()
-        ev.record(main)
+        ev.record(cur)
         self.side.wait_event(ev)
         with torch.cuda.stream(self.side):
             part = self.shard[c0:c1]
             if self.world == 1:
-                self._k0(part, c0, c1 - c0)
+                buf = part.unsqueeze(0)
             else:
-                buf = torch.empty((self.world, c1 - c0, self.d), dtype=torch.float32, device=self.sc.device)
-                dist.all_gather_into_tensor(buf.view(-1, self.d), part.contiguous(), group=self.group)
-                for r in range(self.world):
-                    self._k0(buf[r], r * self.per + c0, c1 - c0)
+                buf = torch.empty((self.world, c1 - c0, self.d_in), dtype=torch.float32, device=self.sc.device)
+                dist.all_gather_into_tensor(buf.view(-1, self.d_in), part, group=self.group)
                 buf.record_stream(self.side)
+            for r in range(self.world):
+                self._k0(buf[r], r * self.per + c0, c1 - c0)
+            if self.labels is not None:
+                self.labels.view(self.world, self.per)[:, c0:c1].copy_(buf[:, :, self.d].view(torch.int32))
         self.staged = c1
 
-    def finish(self) -> Prepared:
-        assert self.filled >= self.r1 - self.r0, "the encoder produced fewer rows than this rank owns"
+    def finish(self, after=None) -> Prepared:
+        """Stages what is left and makes the current stream wait for the staged operands.  after: stream whose queued
+        copies fill the remaining rows (the host->device copy stream)."""
+        assert self.filled >= self.r1 - self.r0, "fewer rows than this rank owns were appended"
+        cur = torch.cuda.current_stream(self.sc.device)
+        if after is not None:
+            cur.wait_stream(after)
         if self.staged < self.per:
             self._stage(self.staged, self.per)
-        torch.cuda.current_stream(self.sc.device).wait_stream(self.side)
+        cur.wait_stream(self.side)
         smax = torch.stack(self.maxima).amax(dim=0)
         n = self.n
         return Prepared(self.f32[:n], self.f16[:n], self.stats[:n], smax, n, self.d, self.d16)

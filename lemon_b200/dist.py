@@ -100,23 +100,28 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
         from .handoff import ShardStager
         cs = _side_stream(dev, "h2d")
         cs.wait_stream(main)
-        st_img = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks)
-        st_txt = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks, LABEL_COLS if with_labels else 0)
+        st_img = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks,
+                             side=_side_stream(dev, "stage_img"))
+        st_txt = ShardStager(scorer, n_total, (r0, r1, per), d, normalize, group, h2d_chunks, LABEL_COLS if with_labels else 0,
+                             side=_side_stream(dev, "stage_txt"))
         step = max(1, -(-per // max(1, h2d_chunks)))
+        e_img, e_txt = torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(cs):
             for a in range(0, per, step):
                 st_img.append(img_local[a:a + step])
+            e_img.record(cs)
             if with_labels:
                 lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
                 st_txt.shard[:, d].copy_(lab.view(torch.float32))
             for a in range(0, per, step):
                 st_txt.append(txt_local[a:a + step], cols=slice(0, d))
-        xdb = st_img.finish(after=cs)
+            e_txt.record(cs)
+        xdb = st_img.finish(after=e_img)
         xdb._pending = scorer.dedup_start(xdb) if getattr(scorer, "dedup", False) else None
         scorer.finish_db(xdb)
 
         def finish_text():
-            ydb = st_txt.finish(after=cs)
+            ydb = st_txt.finish(after=e_txt)
             ydb._pending = scorer.dedup_start(ydb) if getattr(scorer, "dedup", False) else None
             return scorer.finish_db(ydb), st_txt.labels[:n_total] if with_labels else None
         return score_staged(scorer, xdb, None, (r0, r1, per), k=k, metric=metric, hparams=hparams, return_records=return_records,

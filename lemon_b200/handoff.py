@@ -27,7 +27,8 @@ class ShardStager:
     carry that many extra fp32 columns after the embedding (column 0 of them = the int32 label id of the discrete text
     metric); they travel in the same all-gather and K0 reads the embedding columns through its row stride."""
 
-    def __init__(self, scorer, n_total: int, bounds, d: int, normalize: bool, group, chunks: int, label_cols: int = 0):
+    def __init__(self, scorer, n_total: int, bounds, d: int, normalize: bool, group, chunks: int, label_cols: int = 0,
+                 side: "torch.cuda.Stream | None" = None):
         self.sc, self.n, self.group, self.normalize = scorer, n_total, group, normalize
         self.r0, self.r1, self.per = bounds
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -44,7 +45,9 @@ class ShardStager:
         self.maxima = []                                   # one [4] tensor per K0 call
         self.filled = 0                                    # rows written into the shard
         self.staged = 0                                    # rows handed to the side stream
-        self.side = torch.cuda.Stream(dev)
+        # a persistent side stream per role: the caching allocator keeps one pool per stream, a fresh stream per call
+        # would turn every gather buffer into a cudaMalloc
+        self.side = side if side is not None else ldist._side_stream(dev, "stage")
 
     def append(self, rows: torch.Tensor, cols: "slice | None" = None):
         """rows: [b, d_in] (or [b, width of `cols`]) device or pinned host tensor; copied on the CURRENT stream."""
@@ -90,13 +93,13 @@ class ShardStager:
         self.staged = c1
 
     def finish(self, after=None) -> Prepared:
-        """Stages what is left and makes the current stream wait for the staged operands.  after: stream whose queued
-        copies fill the remaining rows (the host->device copy stream)."""
+        """Stages what is left and makes the current stream wait for the staged operands.  after: event recorded behind
+        the copies that fill the remaining rows (the host->device copy stream), needed only when rows are left."""
         assert self.filled >= self.r1 - self.r0, "fewer rows than this rank owns were appended"
         cur = torch.cuda.current_stream(self.sc.device)
-        if after is not None:
-            cur.wait_stream(after)
         if self.staged < self.per:
+            if after is not None:
+                cur.wait_event(after)
             self._stage(self.staged, self.per)
         cur.wait_stream(self.side)
         smax = torch.stack(self.maxima).amax(dim=0)
@@ -124,8 +127,11 @@ def extract_and_score(batches, encode_image, encode_text, n_total: int, *, k: in
             fi = encode_image(image_input)
             ft = encode_text(text_input)
             if st_img is None:
-                st_img = ShardStager(scorer, n_total, bounds, fi.shape[1], normalize, group, gather_chunks)
-                st_txt = ShardStager(scorer, n_total, bounds, ft.shape[1], normalize, group, gather_chunks)
+                dev = scorer.device
+                st_img = ShardStager(scorer, n_total, bounds, fi.shape[1], normalize, group, gather_chunks,
+                                     side=ldist._side_stream(dev, "stage_img"))
+                st_txt = ShardStager(scorer, n_total, bounds, ft.shape[1], normalize, group, gather_chunks,
+                                     side=ldist._side_stream(dev, "stage_txt"))
             st_img.append(fi)
             st_txt.append(ft)
     if st_img is None:

@@ -154,6 +154,9 @@ int lemon_knn_exact(lemon_ctx* ctx, const float* q, const float* db, const int32
  *   outputs (any may be NULL): d1 [nq]; Dn,dists_n,dists_tr_n,Dm,dists_m,dists_tr_m [nq,k] fp32;
  *   In, Im [nq,k] int64 (index_bits = 64, what faiss returns) or int32 (index_bits = 32: half the bytes for
  *   callers that copy the records to the host);  sn, sm, score [nq] float64.
+ *   sides: 3 = everything in one call; 1 = only the image-neighbour side (D_n, dists_n, dists_tr_n, I_n, s_n), 2 = only
+ *   the text-neighbour side plus d_1 and the score, which then reads s_n written by an earlier sides = 1 call on the
+ *   same stream (lets a caller ship the image-side records to the host while the text-side search is still running).
  */
 int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* xdb, const float* ydb,
                 const float* dists_tr, const float* topn_val, const int32_t* topn_idx,
@@ -162,7 +165,7 @@ int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, const float* x
                 const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                 int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
                 float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, void* In,
-                void* Im, int index_bits, double* sn, double* sm, double* score, void* stream);
+                void* Im, int index_bits, int sides, double* sn, double* sm, double* score, void* stream);
 
 /* Score combination only (lib/metrics/utils.py:63-77) on stacked [n,k] fp32 columns. */
 int lemon_combine_scores(lemon_ctx* ctx, const float* Dn, const float* dists_tr_n, const float* dists_n,

@@ -40,7 +40,7 @@ SIGNATURES = {
     "lemon_score": (C.c_int, [C.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_f32p, c_i32p,
                               c_i64p, c_i32p, c_i32p, c_f32p, c_i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.POINTER(C.c_double), c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, C.c_void_p,
-                              C.c_void_p, C.c_int, c_f64p, c_f64p, c_f64p, C.c_void_p]),
+                              C.c_void_p, C.c_int, C.c_int, c_f64p, c_f64p, c_f64p, C.c_void_p]),
     "lemon_hash_rows": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int, c_i64p, C.c_void_p]),
     "lemon_dedup_count_workspace_bytes": (C.c_int64, [C.c_int64]),
     "lemon_dedup_count": (C.c_int, [C.c_void_p, c_f32p, C.c_int64, C.c_int, C.c_void_p, c_i32p, C.c_void_p]),

@@ -20,7 +20,7 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
              const float* __restrict__ class_emb, const int32_t* __restrict__ noisy_label, int n_class, int64_t nq,
              int64_t m, int d, int k, int kp, ScoreHp hp, float* __restrict__ d1, float* __restrict__ Dn, float* __restrict__ dists_n,
              float* __restrict__ dists_tr_n, float* __restrict__ Dm, float* __restrict__ dists_m,
-             float* __restrict__ dists_tr_m, int64_t* __restrict__ In, int64_t* __restrict__ Im, int idx32,
+             float* __restrict__ dists_tr_m, int64_t* __restrict__ In, int64_t* __restrict__ Im, int idx32, int sides,
              double* __restrict__ sn, double* __restrict__ sm, double* __restrict__ score) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warps = int64_t(gridDim.x) * kScWarps;
@@ -58,6 +58,7 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
     double acc_n = 0.0, acc_m = 0.0;
     // lane j (and j+32) keeps neighbour j's record
     for (int side = 0; side < 2; ++side) {
+      if (!((sides >> side) & 1)) continue;     // image-neighbour side = bit 0, text-neighbour side = bit 1
       const float* tv = (side == 0 ? topn_val : topm_val) + row * kp + off;
       const int32_t* ti = (side == 0 ? topn_idx : topm_idx) + row * kp + off;
       const float* other_q = side == 0 ? yr : xr;        // image neighbours -> compare TEXT rows; text neighbours -> IMAGE rows
@@ -126,11 +127,16 @@ score_kernel(const float* __restrict__ xq, const float* __restrict__ yq, const f
       if (side == 0) acc_n = part / double(k); else acc_m = part / double(k);
     }
     if (lane == 0) {
-      if (d1) d1[row] = d1v;
+      // a call that only does the image-neighbour side (sides == 1) leaves d_1 and the score to the call that does the
+      // text side; that call reads s_n back (the two calls are stream-ordered)
+      if (d1 && (sides & 2)) d1[row] = d1v;
       if (hp.has) {
-        if (sn) sn[row] = acc_n;
-        if (sm) sm[row] = acc_m;
-        if (score) score[row] = double(d1v) + hp.beta * acc_n + hp.gamma * acc_m;   // utils.py:77
+        if (sn && (sides & 1)) sn[row] = acc_n;
+        if (sm && (sides & 2)) sm[row] = acc_m;
+        if (score && (sides & 2)) {
+          const double s_n = (sides & 1) ? acc_n : sn[row];
+          score[row] = double(d1v) + hp.beta * s_n + hp.gamma * acc_m;   // utils.py:77
+        }
       }
     }
   }
@@ -179,13 +185,15 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
                            const int32_t* noisy_label, int n_class, int64_t nq, int64_t m, int d, int k,
                            int kp, int metric, const double* hp, float* d1, float* Dn, float* dists_n,
                            float* dists_tr_n, float* Dm, float* dists_m, float* dists_tr_m, void* In,
-                           void* Im, int index_bits, double* sn, double* sm, double* score, void* stream) {
+                           void* Im, int index_bits, int sides, double* sn, double* sm, double* score, void* stream) {
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
-  if (!xq || !yq || !xdb || !ydb || !dists_tr || !topn_val || !topn_idx || !topm_val || !topm_idx || nq < 0 || d <= 0 ||
+  if (!xq || !yq || !xdb || !ydb || !dists_tr || ((sides & 1) && (!topn_val || !topn_idx)) ||
+      ((sides & 2) && (!topm_val || !topm_idx)) || nq < 0 || d <= 0 ||
       k < 1 || k > 64 || (kp != k && kp != k + 1) || (query_in_db && kp != k + 1) || (!query_in_db && kp != k) ||
       ((label_q == nullptr) != (label_db == nullptr)) || ((class_emb == nullptr) != (noisy_label == nullptr)) ||
-      (class_emb && n_class < 1) || (index_bits != 64 && index_bits != 32))
+      (class_emb && n_class < 1) || (index_bits != 64 && index_bits != 32) || sides < 1 || sides > 3 ||
+      (sides == 2 && hp && !sn))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "score: bad args (kp must be k+1 with query_in_db, k without; index_bits 32 or 64)");
   if (nq == 0) return LEMON_OK;
   int64_t blocks = (nq + kScWarps - 1) / kScWarps;
@@ -195,11 +203,11 @@ extern "C" int lemon_score(lemon_ctx* ctx, const float* xq, const float* yq, con
   if (metric == LEMON_METRIC_IP)
     score_kernel<LEMON_METRIC_IP><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
         xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
-        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sn, sm, score);
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sides, sn, sm, score);
   else
     score_kernel<LEMON_METRIC_L2><<<unsigned(blocks), kScWarps * 32, 0, (cudaStream_t)stream>>>(
         xq, yq, xdb, ydb, dists_tr, topn_val, topn_idx, topm_val, topm_idx, query_in_db, label_q, label_db, class_emb, noisy_label, n_class,
-        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sn, sm, score);
+        nq, m, d, k, kp, h, d1, Dn, dists_n, dists_tr_n, Dm, dists_m, dists_tr_m, (int64_t*)In, (int64_t*)Im, index_bits == 32, sides, sn, sm, score);
   ctx->launches++;
   LEMON_CUDA_CHECK(ctx, cudaGetLastError());
   return LEMON_OK;

@@ -167,34 +167,50 @@ def score_staged(scorer, xdb, ydb, bounds, *, k: int, metric: int, hparams=None,
         ydb, lab_db = late_text()
     yq = _slice_prepared(ydb, r0, r1)
     dtr = scorer.rowwise_dist(ydb.f32, xdb.f32, metric)
-    topm = scorer.knn(yq, ydb, kp, metric)
-    info_m = scorer.last_info
     lab_q = lab_db[r0:r1] if lab_db is not None else None
     qid = _global_row_ids(scorer, r0, r1)
     nq = r1 - r0
     common = dict(k=k, kp=kp, metric=metric, qid=qid, lab_q=lab_q, lab_db=lab_db, hparams=hparams,
                   return_records=return_records, index_dtype=index_dtype)
-    if host_out is None or not on_gpu:
-        out = scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, **common)
-    else:
-        # records part by part; the copy stream ships part i to the host while part i+1 is computed
+    stream_out = host_out is not None and on_gpu
+    early = ()
+    if stream_out:
         out_dev = scorer.alloc_outputs(nq, k, hparams, return_records, index_dtype)
         ds = _side_stream(dev, "d2h")
         for name, t in out_dev.items():
             h = host_out.get(name)
             if h is None or h.shape[0] < nq or h.dtype != t.dtype or h.shape[1:] != t.shape[1:]:
                 host_out[name] = torch.empty((per,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
-        parts = max(1, min(int(d2h_parts), nq))
-        step = -(-nq // parts)
-        for a in range(0, nq, step):
-            b = min(nq, a + step)
-            scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, out=out_dev, rows=(a, b), **common)
+        if return_records:
+            # the image-neighbour half of the records only needs the image-side search: it is computed now and shipped
+            # to the host while the text-side search runs
+            scorer.emit(xq, yq, xdb, ydb, dtr, topn, None, out=out_dev, sides=1, **common)
+            early = tuple(c for c in ("D_n", "dists_n", "dists_tr_n", "I_n", "s_n") if c in out_dev)
             ev = torch.cuda.Event()
             ev.record(main)
             ds.wait_event(ev)
             with torch.cuda.stream(ds):
-                for name, t in out_dev.items():
-                    host_out[name][a:b].copy_(t[a:b], non_blocking=True)
+                for name in early:
+                    host_out[name][:nq].copy_(out_dev[name], non_blocking=True)
+    topm = scorer.knn(yq, ydb, kp, metric)
+    info_m = scorer.last_info
+    if not stream_out:
+        out = scorer.emit(xq, yq, xdb, ydb, dtr, topn, topm, **common)
+    else:
+        # the rest part by part; the copy stream ships part i to the host while part i+1 is computed
+        late = [name for name in out_dev if name not in early]
+        parts = max(1, min(int(d2h_parts), nq))
+        step = -(-nq // parts)
+        for a in range(0, nq, step):
+            b = min(nq, a + step)
+            scorer.emit(xq, yq, xdb, ydb, dtr, topn if not early else None, topm, out=out_dev, rows=(a, b),
+                        sides=2 if early else 3, **common)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ds.wait_event(ev)
+            with torch.cuda.stream(ds):
+                for name in late:
+                    host_out[name][a:b].copy_(out_dev[name][a:b], non_blocking=True)
         for t in out_dev.values():
             t.record_stream(ds)
         ds.synchronize()                       # the caller holds the results on the host

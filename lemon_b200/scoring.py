@@ -598,10 +598,11 @@ class LemonScorer:
     def emit(self, xq: Prepared, yq: Prepared, xdb: Prepared, ydb: Prepared, dists_tr, topn, topm, *, k: int, kp: int,
              metric: int, qid=None, lab_q=None, lab_db=None, cls_emb=None, lab_noisy=None, n_class=None,
              hparams: dict | None = None, return_records: bool = True, index_dtype=torch.int64, out: dict | None = None,
-             rows: tuple[int, int] | None = None) -> dict:
+             rows: tuple[int, int] | None = None, sides: int = 3) -> dict:
         """K2b: per-sample records + score from exact top lists (run_lemon.py:250-307, utils.py:63-77).
         `out` = tensors from alloc_outputs to write into; rows=(a, b) processes query rows [a, b) only (callers that
-        stream the results to the host launch it part by part)."""
+        stream the results to the host launch it part by part).  sides: 1 = image-neighbour side only, 2 = text-neighbour
+        side + d_1 + score (after a sides = 1 call), 3 = both (include/lemon_b200.h)."""
         nq = xq.n
         if out is None:
             out = self.alloc_outputs(nq, k, hparams, return_records, index_dtype)
@@ -611,14 +612,15 @@ class LemonScorer:
         assert index_dtype in (torch.int64, torch.int32)
         hp_arr = (C.c_double * 6)(*[float(hparams[key]) for key in HP_KEYS]) if hparams is not None else None
         sl = lambda t: None if t is None else t[a:b]
+        tl = lambda top, i: None if top is None else top[i][a:b]       # a side's top lists may be absent when `sides` skips it
         g = lambda name: _ptr(sl(out.get(name)))
         with torch.cuda.device(self.device):
             self.ctx.check(self.lib.lemon_score(
                 self.ctx.handle, _ptr(xq.f32[a:b]), _ptr(yq.f32[a:b]), _ptr(xdb.f32), _ptr(ydb.f32), _ptr(dists_tr),
-                _ptr(topn[0][a:b]), _ptr(topn[1][a:b]), _ptr(topm[0][a:b]), _ptr(topm[1][a:b]), _ptr(sl(qid)), _ptr(sl(lab_q)),
+                _ptr(tl(topn, 0)), _ptr(tl(topn, 1)), _ptr(tl(topm, 0)), _ptr(tl(topm, 1)), _ptr(sl(qid)), _ptr(sl(lab_q)),
                 _ptr(lab_db), _ptr(cls_emb), _ptr(sl(lab_noisy)), int(n_class or 0), b - a, xdb.n, xdb.d, k, kp, metric, hp_arr,
                 g("d_1"), g("D_n"), g("dists_n"), g("dists_tr_n"), g("D_m"), g("dists_m"), g("dists_tr_m"), g("I_n"), g("I_m"),
-                64 if index_dtype == torch.int64 else 32, g("s_n"), g("s_m"), g("score"), _stream()), "lemon_score")
+                64 if index_dtype == torch.int64 else 32, int(sides), g("s_n"), g("s_m"), g("score"), _stream()), "lemon_score")
         return out
 
     def combine_scores(self, rec: dict, hparams: dict) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:

@@ -94,9 +94,9 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
     main = torch.cuda.current_stream(dev) if on_gpu else None
     metric = METRIC[dist_type]
     if on_gpu and not img_local.is_cuda and d % 4 == 0:
-        # ---- host shards: the copies are cut into chunks on a copy stream; every chunk is all-gathered and normalised
-        # on a side stream as soon as it has landed, so only one chunk of the image copy is exposed and the whole text
-        # side is staged behind the image-side kernels
+        # ---- host shards: the copies are cut into chunks on a copy stream; every IMAGE chunk is all-gathered and
+        # normalised on a side stream as soon as it has landed, so only one chunk of the image copy is exposed; the text
+        # copy runs under the image-side kernels and the text database is staged behind them, on the main stream's order
         from .handoff import ShardStager
         cs = _side_stream(dev, "h2d")
         cs.wait_stream(main)
@@ -114,7 +114,7 @@ def score_pairs_sharded(img_local, txt_local, n_total: int, *, k: int, dist_type
                 lab = torch.as_tensor(text_label_ids_local).to(device=dev, dtype=torch.int32, non_blocking=True)
                 st_txt.shard[:, d].copy_(lab.view(torch.float32))
             for a in range(0, per, step):
-                st_txt.append(txt_local[a:a + step], cols=slice(0, d))
+                st_txt.append(txt_local[a:a + step], cols=slice(0, d), stage=False)
             e_txt.record(cs)
         xdb = st_img.finish(after=e_img)
         xdb._pending = scorer.dedup_start(xdb) if getattr(scorer, "dedup", False) else None

@@ -49,8 +49,11 @@ class ShardStager:
         # would turn every gather buffer into a cudaMalloc
         self.side = side if side is not None else ldist._side_stream(dev, "stage")
 
-    def append(self, rows: torch.Tensor, cols: "slice | None" = None):
-        """rows: [b, d_in] (or [b, width of `cols`]) device or pinned host tensor; copied on the CURRENT stream."""
+    def append(self, rows: torch.Tensor, cols: "slice | None" = None, stage: bool = True):
+        """rows: [b, d_in] (or [b, width of `cols`]) device or pinned host tensor; copied on the CURRENT stream.
+        stage=False only copies: the rows are staged by ``finish`` (used for the text shard of the host-input path: its
+        all-gather must not run beside the image-side search kernel -- a collective that waits for a peer whose SMs are
+        all taken by that persistent kernel would sit on this rank's SMs for the whole search)."""
         b = rows.shape[0]
         assert self.filled + b <= self.per
         dst = self.shard[self.filled:self.filled + b]
@@ -58,7 +61,7 @@ class ShardStager:
         assert rows.shape[1] == dst.shape[1]
         dst.copy_(rows, non_blocking=True)                 # dtype conversion (bf16 autocast -> fp32) included
         self.filled += b
-        while self.filled - self.staged >= self.chunk:
+        while stage and self.filled - self.staged >= self.chunk:
             self._stage(self.staged, self.staged + self.chunk)
 
     def _k0(self, src, row0, nrows):

@@ -92,7 +92,7 @@ int lemon_rowwise_dist(lemon_ctx* ctx, const float* a, const float* b, float* ou
  *   nseg  number of DB segments scanned independently (load balance for small nq); >= 1
  *   Output = LEMON_NLIST(nseg) = nseg * 2 candidate lists per query row (two epilogue warp groups per segment).
  *   nq_pad = nq rounded up to a multiple of 256 rows; the caller allocates all three arrays for nq_pad rows:
- *     cand_keys  [nq_pad, nseg*2, LEMON_LIST_CAP] uint64: key = (order-preserving bits of the approximate inner product) << 32
+ *     cand_keys  [nq_pad, nseg*2, LEMON_LIST_CAP] uint64: key = (IEEE bit pattern of the approximate inner product, fp32) << 32
  *                | ~db_row; only the first cand_cnt entries of a list are valid, in no particular order;
  *                the array must be 8192-byte aligned (one list = 8 KB; LEMON_ERR_INVALID otherwise);
  *     cand_cnt   [nq_pad, nseg*2] int32 (0 .. LEMON_LIST_CAP);

@@ -180,26 +180,32 @@ __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[32]) {
       :
       : "memory");
 }
-// Branch-free survivor append: `if (v > theta) { *p++ = make_key(v, ~nidx); }` as six straight-line instructions
-// (compare, two for the order-preserving bit pattern, one for the index word, predicated 64-bit store, predicated
-// pointer bump).  The compiler's version of the same statement is a divergent branch around a 13-instruction body
-// per element (BSSY / BRA / BSYNC), whose latency -- not its instruction count -- bounded the epilogue.
+// Branch-free survivor append: `if (v > theta) { *p++ = (bits(v) << 32) | ~idx; }` as straight-line instructions
+// (compare, index word, predicated 64-bit store, predicated pointer bump).  The compiler's version of the same
+// statement is a divergent branch around a 13-instruction body per element (BSSY / BRA / BSYNC), whose latency -- not
+// its instruction count -- bounded the epilogue.  The high word is the RAW float bit pattern: the order-preserving
+// transform every sort needs (two more instructions per element, executed for all 32 lanes whether they store or
+// not) is applied by the readers instead (the re-rank kernel, and prune_exact below on the rare full list).
 // Only the low word of the write pointer is bumped: a row's key list is 8 KB and 8 KB-aligned (checked on the
 // host), so it never carries.
 __device__ __forceinline__ void append_if_above(uint64_t& ptr, float v, float theta, uint32_t nidx) {
   asm volatile(
-      "{\n .reg .pred p;\n .reg .b32 t, hi, lo, ph;\n"
+      "{\n .reg .pred p;\n .reg .b32 lo, ph;\n"
       " setp.gt.f32 p, %1, %2;\n"
-      " shr.s32 t, %3, 31;\n"
-      " or.b32 t, t, 0x80000000;\n"
-      " xor.b32 hi, t, %3;\n"
-      " @p st.global.v2.b32 [%0], {%4, hi};\n"
+      " @p st.global.v2.b32 [%0], {%4, %3};\n"
       " mov.b64 {lo, ph}, %0;\n"
       " @p add.u32 lo, lo, 8;\n"
       " mov.b64 %0, {lo, ph};\n}"
       : "+l"(ptr)
       : "f"(v), "f"(theta), "r"(__float_as_uint(v)), "r"(nidx)
       : "memory");
+}
+// list keys in memory carry raw float bits; registers that are sorted carry the order-preserving pattern
+__device__ __forceinline__ uint64_t key_raw_to_ord(uint64_t k) {
+  return k == 0ull ? 0ull : ((uint64_t(f2ord(__uint_as_float(uint32_t(k >> 32)))) << 32) | (k & 0xffffffffull));
+}
+__device__ __forceinline__ uint64_t key_ord_to_raw(uint64_t k) {
+  return k == 0ull ? 0ull : ((uint64_t(__float_as_uint(ord2f(uint32_t(k >> 32)))) << 32) | (k & 0xffffffffull));
 }
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
@@ -317,8 +323,8 @@ __device__ __forceinline__ void prune_exact(uint64_t* b, int& cntL, float& thL, 
     for (int i = 0; i < 4; ++i) {
       const int e = q0 + lane * 8 + 2 * i;
       const ulonglong2 r = __ldcg(reinterpret_cast<const ulonglong2*>(b + e));
-      key[2 * i] = e < cntL ? r.x : 0ull;
-      key[2 * i + 1] = e + 1 < cntL ? r.y : 0ull;
+      key[2 * i] = e < cntL ? key_raw_to_ord(r.x) : 0ull;
+      key[2 * i + 1] = e + 1 < cntL ? key_raw_to_ord(r.y) : 0ull;
     }
     warp_sort256_desc(key, lane);
     if (q0 > 0) {
@@ -336,7 +342,7 @@ __device__ __forceinline__ void prune_exact(uint64_t* b, int& cntL, float& thL, 
   if (lane < kKeep / 8) {
 #pragma unroll
     for (int i = 0; i < 8; i += 2)
-      *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(best[i], best[i + 1]);
+      *reinterpret_cast<ulonglong2*>(b + lane * 8 + i) = make_ulonglong2(key_ord_to_raw(best[i]), key_ord_to_raw(best[i + 1]));
   }
   // cert columns >= the value at rank cert-1 stay in the list: that value is the new threshold
   const float vth = rank_value(best, cert - 1, lane);

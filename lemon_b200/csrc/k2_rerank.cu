@@ -24,7 +24,10 @@ __device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_key
 #pragma unroll
   for (int i = 0; i < kRrPerLane; ++i) {
     const int e = i * 32 + lane;                      // coalesced: consecutive lanes read consecutive keys
-    k[i] = e < c ? __ldg(src + e) : 0ull;
+    // K1 stores the RAW float bits in the high word (its append runs for all 32 lanes of a warp); everything below
+    // compares keys, so the order-preserving pattern is applied here
+    const uint64_t raw = e < c ? __ldg(src + e) : 0ull;
+    k[i] = raw == 0ull ? 0ull : ((uint64_t(f2ord(__uint_as_float(uint32_t(raw >> 32)))) << 32) | (raw & 0xffffffffull));
   }
 }
 

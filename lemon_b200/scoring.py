@@ -84,10 +84,9 @@ def decode_candidates(cand_keys: torch.Tensor, cand_cnt: torch.Tensor, n_rows: i
     c = cand_cnt[:n_rows].cpu().numpy()
     n, nlist, cap = k.shape
     valid = np.arange(cap)[None, None, :] < c[:, :, None]
-    hi = (k >> np.uint64(32)).astype(np.uint32)
+    hi = (k >> np.uint64(32)).astype(np.uint32)          # raw fp32 bit pattern of the approximate value
     lo = (k & np.uint64(0xffffffff)).astype(np.uint32)
-    bits = np.where(hi >> 31, hi ^ np.uint32(0x80000000), ~hi)
-    vals = bits.view(np.float32).astype(np.float32)
+    vals = hi.view(np.float32).astype(np.float32)
     idx = (~lo).astype(np.int64)
     vals = np.where(valid, vals, -np.inf).reshape(n, -1)
     idx = np.where(valid, idx, -1).reshape(n, -1)

@@ -495,7 +495,7 @@ def test_many_segments_stay_certified(lb, m, nseg, keep):
     # least `keep` columns at or above the larger of their two thresholds
     k64 = ck[:nq].cpu().numpy().view(np.uint64)
     hi = (k64 >> np.uint64(32)).astype(np.uint32)
-    vals = np.where(hi >> 31, hi ^ np.uint32(0x80000000), ~hi).view(np.float32)
+    vals = hi.view(np.float32)                                                # K1 stores the raw fp32 bit pattern
     cnt, th = cc[:nq].cpu().numpy(), ct[:nq].cpu().numpy()
     valid = np.arange(1024)[None, None, :] < cnt[:, :, None]
     th_seg = th.reshape(nq, nseg, 2).max(-1)                                  # [nq, nseg]

@@ -173,32 +173,44 @@ def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512)
     return best
 
 
-def plan_tail(nq: int, m: int, num_sms: int, cta_group: int) -> tuple[int, int]:
+def plan_tail(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512) -> tuple[int, int]:
     """Wave-quantisation fix for the tensor-core kernel.  Its work items are 128*cta_group-row query tiles
-    dealt to num_sms/cta_group CTA (pairs); when the last round is mostly empty, the rows of that round are
-    searched by a second launch with the DB split into segments so that every CTA pair gets a (short) item.
-    Returns (rows of the main launch, segments of the tail launch); (nq, 1) means one launch."""
+    dealt to num_sms/cta_group CTA (pairs); when the last round is not full, the rows of that round are searched by a
+    second launch with the DB split into segments, so that its items fill whole (shorter) waves.  The number of
+    segments minimises waves * (columns per segment + per-wave overhead), the cost model of plan_segments, and the
+    split must save at least 10 % of a round.  Databases beyond ~1 GB of fp16 keep the round-1 rule (split only a
+    mostly empty last round): a segmented launch walks its segments unpaced, and at that size every pair would stream
+    its segment from DRAM.  Returns (rows of the main launch, segments of the tail launch); (nq, 1) means one launch."""
     units = max(1, num_sms // cta_group)
     rows_per_tile = 128 * cta_group
     tiles = -(-nq // rows_per_tile)
     full = (tiles // units) * units
     tail = tiles - full
-    if full == 0 or tail == 0 or tail > 0.6 * units:
+    if full == 0 or tail == 0:
         return nq, 1
-    nseg = min(units // tail, 16)
-    while nseg > 1 and m // nseg < 4096:
-        nseg -= 1
-    if nseg <= 1:
+    if 2.0 * m * d16 > 1.0e9 and tail > 0.6 * units:
         return nq, 1
-    return full * rows_per_tile, nseg
+    overhead_cols = 6000.0
+    best, best_cost = 1, m + overhead_cols
+    for nseg in range(2, 17):
+        if m // nseg < 4096:
+            break
+        waves = -(-(tail * nseg) // units)
+        cost = waves * (m / nseg + overhead_cols)
+        if cost < best_cost:
+            best, best_cost = nseg, cost
+    if best == 1 or best_cost > 0.9 * (m + overhead_cols):
+        return nq, 1
+    return full * rows_per_tile, best
 
 
-def plan_parts(nq: int, m: int, num_sms: int, cta_group: int, max_rows: int = 1 << 19) -> list[tuple[int, int, int | None]]:
+def plan_parts(nq: int, m: int, num_sms: int, cta_group: int, max_rows: int = 1 << 19,
+               d16: int = 512) -> list[tuple[int, int, int | None]]:
     """K1 launches of one kNN call as (row0, row1, nseg or None = planner's choice).  The main part is cut into
     whole rounds of query tiles (one round = one 128*cta_group-row tile per CTA pair, so every cut launch is as
     efficient as the uncut one) of at most `max_rows` rows: a launch's candidate lists take 2 * 8 KB per row, which
     bounds them to ~8.6 GB however many query rows there are.  The tail part comes from plan_tail."""
-    n_main, nseg_tail = plan_tail(nq, m, num_sms, cta_group)
+    n_main, nseg_tail = plan_tail(nq, m, num_sms, cta_group, d16)
     round_rows = max(1, num_sms // cta_group) * 128 * cta_group
     step = max(1, max_rows // round_rows) * round_rows
     parts: list[tuple[int, int, int | None]] = []
@@ -210,7 +222,7 @@ def plan_parts(nq: int, m: int, num_sms: int, cta_group: int, max_rows: int = 1 
             parts.append((a, b, None if len(cuts) == 2 else 1))
         if len(parts) > 1:                                          # the last piece may again want a tail split
             a, b, _ = parts.pop()
-            nm2, ns2 = plan_tail(b - a, m, num_sms, cta_group)
+            nm2, ns2 = plan_tail(b - a, m, num_sms, cta_group, d16)
             parts += [(a, b, None)] if nm2 >= b - a else [(a, a + nm2, 1), (a + nm2, b, ns2)]
         return parts
     for a in range(0, n_main, step):
@@ -488,7 +500,7 @@ class LemonScorer:
         top_val = torch.empty((q.n, kp), dtype=torch.float32, device=self.device)
         top_idx = torch.empty((q.n, kp), dtype=torch.int32, device=self.device)
         cg = self.cta_group if self.cta_group else 2
-        parts = plan_parts(q.n, db.n, self.num_sms, cg)
+        parts = plan_parts(q.n, db.n, self.num_sms, cg, d16=db.d16)
         pending, nsegs = [], []
         for r0, r1, ns in parts:
             qs = q if (r0 == 0 and r1 == q.n) else _slice_prepared(q, r0, r1)

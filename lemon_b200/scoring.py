@@ -151,16 +151,18 @@ def plan_segments(nq: int, m: int, num_sms: int, cta_group: int, d16: int = 512)
     row and segment for the re-rank and of a fixed cost per wave of items.  Calibrated on B200 with the round-2 kernel
     (profiles/r02_plan_calibrate.log): a wave costs its columns plus ~0.08 ms (d = 512) / ~0.14 ms (d = 768), i.e. the
     MMA time of ~6000 columns either way; one row tile against 370 000 columns: 5.1 ms unsplit, 0.42 ms in 16
-    segments, 0.16 ms in 64.  Launches of two or more full rounds are never split (their lists would double for a gain
+    segments, 0.25 ms in 32, 0.16 ms in 64.  Launches of two or more full rounds are never split (their lists would double for a gain
     the tail launch of plan_tail gets more cheaply, and only unsplit launches pace their DB walk)."""
     units = max(1, num_sms // cta_group)
     tiles = max(1, -(-nq // (128 * cta_group)))
     if tiles >= 2 * units:
         return 1
     overhead_cols = 6000.0
-    cands = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 64}
+    # at most 32 segments: beyond that the re-rank's walk over 2 * nseg lists per row and the candidate-list allocation
+    # cost what the shorter K1 items save (profiles/r02_seam1_search_nq128.log: 0.70 ms per 128-query call at 32)
+    cands = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32}
     if tiles < units:
-        cands.add(min(64, units // tiles))          # exactly one wave
+        cands.add(min(32, units // tiles))          # exactly one wave
     best, best_cost = 1, None
     for nseg in sorted(cands):
         if nseg > 1 and m // nseg < 4096:

@@ -88,9 +88,9 @@ def test_plan_segments():
     for nq in (1, 1000, 50_000):
         for m in (10, 50_000, 3_300_000):
             n = plan_segments(nq, m, 148, 2, 512)
-            assert 1 <= n <= 64 and (n == 1 or m // n >= 4096)
+            assert 1 <= n <= 32 and (n == 1 or m // n >= 4096)
     # calibration points (profiles/r02_plan_calibrate.log): one row tile wants one full wave of short items
-    assert plan_segments(128, 370_000, 148, 2, 512) == 64 and plan_segments(1024, 370_000, 148, 2, 512) in (16, 18)
+    assert plan_segments(128, 370_000, 148, 2, 512) == 32 and plan_segments(1024, 370_000, 148, 2, 512) in (16, 18)
     assert plan_segments(4096, 370_000, 148, 2, 512) == 4 and plan_segments(8448, 370_000, 148, 2, 512) == 2
     assert plan_segments(128, 50_000, 148, 2, 512) in (8, 12)
 

@@ -276,3 +276,24 @@ def test_second_pass_rescues_rows_the_fp16_pass_cannot_certify(lb):
     finally:
         sc.second_pass_enabled = True
     assert (ti0 == ei).all() and (tv0 == ev).all()
+
+
+@pytest.mark.parametrize("metric,kp", [(1, 31), (0, 51), (1, 51)])
+def test_second_pass_other_metrics_and_list_lengths(lb, metric, kp):
+    """The split-precision pass under the squared-L2 metric and with the longest lists LEMoN uses (k = 50, train split):
+    hard rows get certified (or fall through to the exact kernel) and the lists stay bitwise those of the exact kernel."""
+    import torch
+    from lemon_b200.scoring import count_uncertified
+    dev = torch.device("cuda", 0)
+    x = _narrow_cone(60_000, 512, 0.98, 13, dev)
+    sc = lb.get_scorer(0)
+    dbp = sc.prepare(x, True)
+    qp = lemon_slice(dbp, 1000, 3048)
+    tv, ti = sc.knn(qp, dbp, kp, metric, mode="tc")
+    info = dict(sc.last_info)
+    ev, ei = sc.knn(qp, dbp, kp, metric, mode="exact")
+    assert (ti == ei).all() and (tv == ev).all()
+    print("metric %d kp %d: first pass uncertified %d of 2048, to the exact kernel %d" %
+          (metric, kp, info["n_uncertified_first_pass"], count_uncertified(info)))
+    if metric == 0:
+        assert info["n_uncertified_first_pass"] > 100 and count_uncertified(info) <= info["n_uncertified_first_pass"] // 10

@@ -138,3 +138,32 @@ def test_plan_parts_bounds_candidate_memory():
         n_main, nseg_tail = plan_tail(nq, m, 148, 2)
         if n_main < nq:
             assert parts[-1] == (n_main, nq, nseg_tail)
+
+
+def test_db_cap_helpers_follow_the_reference():
+    """run_lemon.py:122-127 (np.random.choice without replacement when the split exceeds the cap, arange otherwise) and
+    :258,278 (membership of the sample in train_indices_in_compr) as one scatter; same answers as the oracle's."""
+    import numpy as np
+    import lemon_b200
+    from oracle import lemon_oracle as O
+    assert (lemon_b200.subsample_db(100, 50_000) == np.arange(100)).all()
+    a = lemon_b200.subsample_db(1000, 300, np.random.RandomState(4))
+    b = O.subsample_db(1000, 300, np.random.RandomState(4))
+    assert (a == b).all() and len(set(a.tolist())) == 300 and not (np.diff(a) > 0).all()
+    np.random.seed(81)                                            # run_lemon.py:81 seeds the GLOBAL numpy RNG
+    c = lemon_b200.subsample_db(1000, 300)
+    np.random.seed(81)
+    assert (c == np.random.choice(np.arange(1000), 300, replace=False)).all()
+    qid = lemon_b200.query_in_db_from_indices(1000, a)
+    assert (qid == O.query_in_db_from_indices(1000, a)).all()
+    for s in (0, 17, 999):
+        assert (qid[s] >= 0) == (s in a) and (qid[s] < 0 or a[qid[s]] == s)
+
+
+def test_accumulation_bounds():
+    from lemon_b200.scoring import acc_eps_coef, acc_eps_coef_split
+    assert abs(acc_eps_coef(768, 768) - (768 * 2.0 ** -23 + 30 * 2.0 ** -24)) < 1e-12       # gamma_n with truncating adds
+    assert acc_eps_coef(512, 512) < acc_eps_coef(768, 768)
+    # the split pass accumulates the two small cross terms first: its bound stays that of ONE d16-long product
+    assert acc_eps_coef_split(768, 768) < 1.02 * acc_eps_coef(768, 768) + 2.0 ** -21
+    assert acc_eps_coef_split(768, 768) < 0.4 * acc_eps_coef(3 * 768, 768)

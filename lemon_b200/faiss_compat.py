@@ -63,16 +63,17 @@ class _IndexFlat:
         k = int(k)
         nq = xt.shape[0]
         sc = self._sc()
-        fill = float("-inf") if self.metric_type == METRIC_INNER_PRODUCT else float("inf")
-        D = torch.full((nq, k), fill, dtype=torch.float32, device=sc.device)
-        I = torch.full((nq, k), -1, dtype=torch.int64, device=sc.device)
+        if k > 64:
+            raise RuntimeError("lemon_b200.faiss_compat: k > 64 is not supported")
         if self.ntotal > 0 and nq > 0:
             q = sc.prepare(xt, normalize=False)
-            if k > 64:
-                raise RuntimeError("lemon_b200.faiss_compat: k > 64 is not supported")
-            tv, ti = sc.knn(q, self._db(), k, self.metric_type)
-            D[:, :k] = tv
-            I[:, :k] = ti.to(torch.int64)
+            # the kernels already pad like faiss (I = -1, D = -inf / +inf when ntotal < k): the lists ARE the answer
+            D, ti = sc.knn(q, self._db(), k, self.metric_type)
+            I = ti.to(torch.int64)
+        else:
+            fill = float("-inf") if self.metric_type == METRIC_INNER_PRODUCT else float("inf")
+            D = torch.full((nq, k), fill, dtype=torch.float32, device=sc.device)
+            I = torch.full((nq, k), -1, dtype=torch.int64, device=sc.device)
         if was_numpy or not xt.is_cuda:
             return D.cpu().numpy(), I.cpu().numpy()
         return D, I

@@ -541,8 +541,10 @@ class LemonScorer:
     def set_database(self, img_db, txt_db, dist_type: str = "cosine", normalize: bool = True,
                      text_label_ids_db=None):
         metric = METRIC[dist_type]
-        xdb = self.prepare_db(img_db, normalize)
-        ydb = self.prepare_db(txt_db, normalize)
+        xdb = self.prepare_db(img_db, normalize, defer_dedup=True)
+        ydb = self.prepare_db(txt_db, normalize, defer_dedup=True)
+        self.finish_db(xdb)           # both duplicate counts are queued by now: one host round trip reads them
+        self.finish_db(ydb)
         assert xdb.n == ydb.n and xdb.d == ydb.d
         self.db = {"x": xdb, "y": ydb, "metric": metric, "normalize": normalize,
                    "dists_tr": self.rowwise_dist(ydb.f32, xdb.f32, metric),

@@ -7,10 +7,12 @@
 //   warp 1    MMA issuer   : tcgen05.mma kind::f16, 128(x2) x BN x 16 per instruction, accumulators
 //                             double-buffered in TMEM (512 columns)
 //   warp 2    TMEM alloc / dealloc
+//   warp 3    pacer (leader CTA): keeps the CTA pairs within an L2-sized window of the slowest pair's DB position,
+//                             so that a DB tile is fetched from DRAM once and not once per pair ("DB-walk pacing" below)
 //   warps 4-11 epilogue    : two groups of four warps; group g scans column half g of EVERY accumulator tile
 //                             (so a buffer is held for half a scan time and no group idles while "its" buffer
 //                             is being refilled).  tcgen05.ld 32x32b (thread == query row), FMNMX3 max tree
-//                             against the row's threshold, survivors appended branch-free as 64-bit keys to the
+//                             against the row's threshold, survivors appended branch-free as 64-bit keys (raw float bits | ~row) to the
 //                             row's 1024-slot list (which lives in the OUTPUT array); the row thresholds rise by
 //                             a counting ladder (no sorting or compaction during the scan), are shared between
 //                             the groups and bootstrapped from group maxima.

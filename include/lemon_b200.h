@@ -109,7 +109,8 @@ int lemon_knn_candidates(lemon_ctx* ctx, const void* q16, const void* db16, int6
                          float* cand_theta, void* stream);
 
 /* fp32 exact re-rank of the candidates + per-row certificate (K2a).
- *   q [nq, d], db [m, d] fp32;  cand_* from lemon_knn_candidates with nlist = nseg*2 lists per row.
+ *   q [nq, d], db [m, d] fp32;  cand_* from lemon_knn_candidates with nlist = nseg*2 lists per row (nlist <= 64, i.e. at
+ *   most 32 segments).
  *   The kernel first selects the row's 64 best approximate candidates over the union of its lists, drops those
  *   that provably cannot be in the exact top-kp, gathers the rest and evaluates them exactly in fp32.
  *   q_row_stats [nq,4], db_stats_max [4]: outputs of lemon_normalize_cast for the query rows and the DB.

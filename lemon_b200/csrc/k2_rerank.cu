@@ -15,11 +15,15 @@ constexpr int kRrChunk = 256;
 constexpr int kRrPerLane = kRrChunk / 32;
 constexpr int kRrChunksPerList = kListCap / kRrChunk;
 static_assert(kListCap % kRrChunk == 0, "candidate lists are read in 256-key chunks");
-__device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_keys, const int32_t* __restrict__ cand_cnt,
+// cnt_lo / cnt_hi: the lengths of the row's lists, list l in lane l & 31 (loaded once per row: the key loads of a chunk
+// then do not wait for a dependent length load first)
+__device__ __forceinline__ void load_chunk(const uint64_t* __restrict__ cand_keys, int cnt_lo, int cnt_hi,
                                            int64_t row, int nlist, int chunk, int lane, uint64_t (&k)[kRrPerLane], int& tot) {
   const int l = chunk / kRrChunksPerList, part = chunk % kRrChunksPerList;
-  const int c = max(0, min(min(cand_cnt[row * nlist + l], kListCap) - part * kRrChunk, kRrChunk));
+  const int len = __shfl_sync(kFull, l < 32 ? cnt_lo : cnt_hi, l & 31);
+  const int c = max(0, min(min(len, kListCap) - part * kRrChunk, kRrChunk));
   tot = c;
+  if (c == 0) return;
   const uint64_t* src = cand_keys + (row * nlist + l) * kListCap + part * kRrChunk;
 #pragma unroll
   for (int i = 0; i < kRrPerLane; ++i) {
@@ -105,8 +109,10 @@ rerank_kernel(const float* __restrict__ q, const float* __restrict__ db, const u
     };
     uint64_t k[kRrPerLane];
     int tot;
+    const int cnt_lo = lane < nlist ? cand_cnt[row * nlist + lane] : 0;
+    const int cnt_hi = lane + 32 < nlist ? cand_cnt[row * nlist + lane + 32] : 0;
     for (int c = 0; c < nchunk; ++c) {
-      load_chunk(cand_keys, cand_cnt, row, nlist, c, lane, k, tot);
+      load_chunk(cand_keys, cnt_lo, cnt_hi, row, nlist, c, lane, k, tot);
       if (tot == 0) continue;
 #pragma unroll
       for (int i = 0; i < kRrPerLane; ++i) {
@@ -199,7 +205,7 @@ extern "C" int lemon_rerank(lemon_ctx* ctx, const float* q, const float* db, con
   using namespace lemon;
   if (!ctx) return LEMON_ERR_INVALID;
   if (!q || !db || !cand_keys || !cand_cnt || !cand_theta || !top_val || !top_idx || !uncert_rows || !n_uncert || nq < 0 ||
-      d <= 0 || kp < 1 || kp > LEMON_MAX_KP || nlist < 1 || (q_row_stats && !db_stats_max))
+      d <= 0 || kp < 1 || kp > LEMON_MAX_KP || nlist < 1 || nlist > 64 || (q_row_stats && !db_stats_max))
     return lemon_set_error(ctx, LEMON_ERR_INVALID, "rerank: bad args");
   LEMON_CUDA_CHECK(ctx, cudaMemsetAsync(n_uncert, 0, sizeof(int32_t), (cudaStream_t)stream));
   if (nq == 0) return LEMON_OK;

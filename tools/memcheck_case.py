@@ -1,6 +1,8 @@
 """Small run of every NON-tensor-core kernel of the library for `compute-sanitizer --tool memcheck` (the persistent tcgen05
 kernel is left out on purpose: it spins on mbarriers and would crawl under instrumentation):
-    timeout 600 compute-sanitizer --tool memcheck python tools/memcheck_case.py"""
+    timeout 600 compute-sanitizer --tool memcheck python tools/memcheck_case.py
+(compute-sanitizer was closed on the round-2 GPU pool, so this case was not run under it; without the tool it is a
+plain smoke run of those kernels)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
